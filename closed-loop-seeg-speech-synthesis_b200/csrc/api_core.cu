@@ -1,0 +1,112 @@
+// Library plumbing: error reporting, host/device buffer staging, scratch memory, init.
+#include <stdarg.h>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+#include "../../include/sgs.h"
+
+namespace sgs {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return SGS_ERR_CUDA;
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int stage_in(Staged& s, const void* p, size_t bytes, cudaStream_t st) {
+    s = Staged();
+    s.bytes = bytes;
+    if (bytes == 0) return SGS_OK;
+    if (is_device_ptr(p)) { s.dev = const_cast<void*>(p); return SGS_OK; }
+    s.host = const_cast<void*>(p);
+    SGS_CUDA(cudaMallocAsync(&s.dev, bytes, st));
+    s.owned = true;
+    SGS_CUDA(cudaMemcpyAsync(s.dev, p, bytes, cudaMemcpyHostToDevice, st));
+    return SGS_OK;
+}
+
+int stage_out(Staged& s, void* p, size_t bytes, cudaStream_t st) {
+    s = Staged();
+    s.bytes = bytes;
+    if (bytes == 0) return SGS_OK;
+    if (is_device_ptr(p)) { s.dev = p; return SGS_OK; }
+    s.host = p;
+    SGS_CUDA(cudaMallocAsync(&s.dev, bytes, st));
+    s.owned = true;
+    return SGS_OK;
+}
+
+int finish_out(Staged& s, cudaStream_t st) {
+    if (s.host && s.bytes) SGS_CUDA(cudaMemcpyAsync(s.host, s.dev, s.bytes, cudaMemcpyDeviceToHost, st));
+    return SGS_OK;
+}
+
+void release(Staged& s, cudaStream_t st) {
+    if (s.owned && s.dev) cudaFreeAsync(s.dev, st);
+    s = Staged();
+}
+
+}  // namespace sgs
+
+extern "C" {
+
+int sgs_abi_version(void) { return SGS_ABI_VERSION; }
+const char* sgs_last_error(void) { return sgs::g_err; }
+unsigned long long sgs_launch_count(void) { return sgs::g_launches; }
+
+int sgs_device_count(int* count) {
+    SGS_ARG(count != nullptr, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return sgs::cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+    return SGS_OK;
+}
+
+int sgs_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        sgs::set_error("no CUDA device available (libsgs has no CPU fallback)");
+        return SGS_ERR_CUDA;
+    }
+    SGS_ARG(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    SGS_CUDA(cudaSetDevice(device));
+    SGS_CUDA(cudaFree(0));
+    cudaDeviceProp p;
+    SGS_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        sgs::set_error("libsgs is built for sm_100a only; device %d is sm_%d%d", device, p.major, p.minor);
+        return SGS_ERR_UNSUPPORTED;
+    }
+    // keep freed stream-ordered scratch around instead of returning it to the OS after every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return SGS_OK;
+}
+
+int sgs_synchronize(void* stream) {
+    SGS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return SGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+// C ABI for feature extraction (include/sgs.h).
+#include <vector>
+#include "feat.cuh"
+#include "../../include/sgs.h"
+
+namespace sgs {
+int feat_run(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* carry, const double* phi,
+             bool apply_phi, const long long* bounds, const int* kfirst, const int* starts, const double* zf,
+             const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st);
+int stack_run(const double* feat, double* out, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,
+              int order, int step, cudaStream_t st);
+}  // namespace sgs
+
+struct sgs_feat_plan {
+    int n_biquads = 0;
+    bool monic = false;
+    int zero_fill = 0;
+    sgs::FeatCoefs cf;
+    double* d_zf = nullptr;               // zero-fill response table on the device
+    // cached window table (re-uploaded only when the caller's table changes)
+    std::vector<int32_t> h_starts;
+    int32_t* d_starts = nullptr;
+    size_t d_starts_cap = 0;
+};
+
+extern "C" {
+
+int sgs_feat_plan_create(sgs_feat_plan** plan, int n_filters, const double* coef, const double* zi_unit,
+                         const double* zi_last_warm, const double* zero_fill_response, int zero_fill) {
+    SGS_ARG(plan && coef && zi_unit && zi_last_warm, "NULL argument");
+    SGS_ARG(n_filters == 2 || n_filters == 3, "n_filters must be 2 or 3 (got %d)", n_filters);
+    SGS_ARG(zero_fill >= 0 && (zero_fill == 0 || zero_fill_response), "zero_fill table missing");
+    sgs_feat_plan* p = new sgs_feat_plan();
+    p->n_biquads = n_filters * sgs::kSecPerFilter;
+    p->zero_fill = zero_fill;
+    memset(&p->cf, 0, sizeof(p->cf));
+    bool monic = true;
+    for (int i = 0; i < p->n_biquads; ++i) {
+        for (int k = 0; k < 5; ++k) p->cf.c[i][k] = coef[i * 5 + k];
+        p->cf.zi[i][0] = zi_unit[i * 2];
+        p->cf.zi[i][1] = zi_unit[i * 2 + 1];
+        if (i % sgs::kSecPerFilter != 0 && !(coef[i * 5] == 1.0 && coef[i * 5 + 2] == 1.0)) monic = false;
+    }
+    p->monic = monic;
+    for (int s = 0; s < sgs::kSecPerFilter; ++s) {
+        p->cf.zi_warm[s][0] = zi_last_warm[s * 2];
+        p->cf.zi_warm[s][1] = zi_last_warm[s * 2 + 1];
+    }
+    if (zero_fill > 0) {
+        cudaError_t e = cudaMalloc(&p->d_zf, sizeof(double) * zero_fill);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_zf, zero_fill_response, sizeof(double) * zero_fill, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { delete p; return sgs::cuda_fail(e, "zero-fill table upload", __FILE__, __LINE__); }
+    }
+    *plan = p;
+    return SGS_OK;
+}
+
+void sgs_feat_plan_destroy(sgs_feat_plan* p) {
+    if (!p) return;
+    if (p->d_zf) cudaFree(p->d_zf);
+    if (p->d_starts) cudaFree(p->d_starts);
+    delete p;
+}
+
+int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_samples, int n_channels, int n_sessions,
+                     int64_t session_stride, const int32_t* win_starts, int n_windows, int window_len, int n_chunks,
+                     int64_t chunk_len, int horizon, const double* phi, double* feat, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(p && x && feat, "NULL argument");
+    SGS_ARG(n_samples >= 1 && n_channels >= 1 && n_sessions >= 1, "empty input");
+    SGS_ARG(n_windows >= 0 && window_len >= 1, "bad window table");
+    if (n_windows == 0) return SGS_OK;
+    SGS_ARG(win_starts != nullptr, "win_starts is NULL");
+    SGS_ARG(n_chunks >= 1 && (n_chunks == 1 || (chunk_len >= 1 && (int64_t)(n_chunks - 1) * chunk_len < n_samples)),
+            "bad chunk plan (%d chunks of %lld over %lld samples)", n_chunks, (long long)chunk_len, (long long)n_samples);
+    const bool apply_phi = n_chunks > 2 && horizon >= chunk_len;
+    SGS_ARG(!apply_phi || phi != nullptr, "phi = A^chunk_len is required when horizon >= chunk_len");
+    SGS_ARG(n_chunks == 1 || horizon >= 1, "horizon must be >= 1");
+    if (session_stride == 0) session_stride = n_samples * n_channels;
+    // validate the window table on the host (it is O(frames), tiny next to the sample data)
+    for (int k = 0; k < n_windows; ++k) {
+        SGS_ARG(k == 0 || win_starts[k] > win_starts[k - 1], "win_starts must be strictly increasing (k=%d)", k);
+        SGS_ARG(k + kFifo >= n_windows || win_starts[k + kFifo] >= win_starts[k] + window_len,
+                "more than %d windows open at once (k=%d)", kFifo, k);
+    }
+    SGS_ARG(win_starts[0] >= -p->zero_fill, "first window starts before the zero-fill region");
+    SGS_ARG((int64_t)win_starts[n_windows - 1] + window_len <= n_samples, "last window ends past the input");
+    const int t_first = win_starts[0] < 0 ? win_starts[0] : 0;
+
+    // chunk bounds + window ownership (by window start)
+    std::vector<long long> bounds(n_chunks + 1);
+    for (int j = 0; j < n_chunks; ++j) bounds[j] = (long long)j * chunk_len;
+    bounds[n_chunks] = n_samples;
+    std::vector<int> kfirst(n_chunks + 1);
+    {
+        int k = 0;
+        kfirst[0] = 0;
+        for (int j = 1; j < n_chunks; ++j) {
+            while (k < n_windows && win_starts[k] < bounds[j]) ++k;
+            kfirst[j] = k;
+        }
+        kfirst[n_chunks] = n_windows;
+    }
+
+    // window table upload (cached)
+    if (p->h_starts.size() != (size_t)n_windows || memcmp(p->h_starts.data(), win_starts, sizeof(int32_t) * n_windows) != 0) {
+        if (p->d_starts_cap < (size_t)n_windows) {
+            SGS_CUDA(cudaStreamSynchronize(st));
+            if (p->d_starts) SGS_CUDA(cudaFree(p->d_starts));
+            SGS_CUDA(cudaMalloc(&p->d_starts, sizeof(int32_t) * n_windows));
+            p->d_starts_cap = n_windows;
+        }
+        p->h_starts.assign(win_starts, win_starts + n_windows);
+        SGS_CUDA(cudaMemcpyAsync(p->d_starts, p->h_starts.data(), sizeof(int32_t) * n_windows, cudaMemcpyHostToDevice, st));
+    }
+
+    FeatGeom g;
+    g.n_samples = n_samples;
+    g.n_channels = n_channels;
+    g.n_sessions = n_sessions;
+    g.session_stride = session_stride;
+    g.n_streams = n_channels * n_sessions;
+    g.n_windows = n_windows;
+    g.window_len = window_len;
+    g.t_first = t_first;
+    g.zero_fill = p->zero_fill;
+    g.n_chunks = n_chunks;
+    g.horizon = horizon;
+    g.state_stride = g.n_streams;
+
+    const size_t esz = x_is_f64 ? 8 : 4;
+    const size_t x_bytes = ((size_t)(n_sessions - 1) * session_stride + (size_t)n_samples * n_channels) * esz;
+    const size_t f_bytes = (size_t)n_sessions * n_windows * n_channels * sizeof(double);
+    Staged sx, sf;
+    int rc = stage_in(sx, x, x_bytes, st);
+    if (rc) return rc;
+    rc = stage_out(sf, feat, f_bytes, st);
+    if (rc) { release(sx, st); return rc; }
+
+    // small per-call tables + carry scratch, stream-ordered
+    const int ns = 2 * p->n_biquads;
+    const size_t tab_bytes = sizeof(long long) * (n_chunks + 1) + sizeof(int) * (n_chunks + 1) + (apply_phi ? sizeof(double) * ns * ns : 0);
+    const size_t carry_bytes = n_chunks > 1 ? sizeof(double) * (size_t)(n_chunks - 1) * ns * g.n_streams : 0;
+    char* d_tab = nullptr;
+    double* d_carry = nullptr;
+    std::vector<char> h_tab(tab_bytes);
+    size_t off_k = sizeof(long long) * (n_chunks + 1), off_phi = off_k + sizeof(int) * (n_chunks + 1);
+    off_phi = (off_phi + 7) & ~(size_t)7;
+    h_tab.resize(off_phi + (apply_phi ? sizeof(double) * ns * ns : 0));
+    memcpy(h_tab.data(), bounds.data(), sizeof(long long) * (n_chunks + 1));
+    memcpy(h_tab.data() + off_k, kfirst.data(), sizeof(int) * (n_chunks + 1));
+    if (apply_phi) memcpy(h_tab.data() + off_phi, phi, sizeof(double) * ns * ns);
+    cudaError_t e = cudaMallocAsync((void**)&d_tab, h_tab.size(), st);
+    if (e == cudaSuccess && carry_bytes) e = cudaMallocAsync((void**)&d_carry, carry_bytes, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, h_tab.data(), h_tab.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { release(sx, st); release(sf, st); return cuda_fail(e, "scratch", __FILE__, __LINE__); }
+    // the pageable h_tab copy above is staged synchronously by the runtime, so h_tab may go out of scope
+
+    rc = feat_run(p->n_biquads, p->monic, sx.dev, x_is_f64 != 0, (double*)sf.dev, d_carry, (const double*)(d_tab + off_phi),
+                  apply_phi, (const long long*)d_tab, (const int*)(d_tab + off_k), p->d_starts, p->d_zf, p->cf, g, st);
+    if (rc == SGS_OK) rc = finish_out(sf, st);
+    cudaFreeAsync(d_tab, st);
+    if (d_carry) cudaFreeAsync(d_carry, st);
+    const bool sync = sf.host != nullptr;
+    release(sx, st);
+    release(sf, st);
+    if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int sgs_feat_stack(const double* feat, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,
+                   int order, int step, double* out, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(n_sessions >= 1 && n_windows >= 0 && n_channels >= 1 && order >= 0 && step >= 1, "bad shape");
+    if (n_rows <= 0) return SGS_OK;
+    SGS_ARG(feat && out, "NULL argument");
+    SGS_ARG(first_row >= 0 && first_row + n_rows <= n_windows, "rows [%d, %d) outside the %d windows", first_row, first_row + n_rows, n_windows);
+    Staged sf, so;
+    int rc = stage_in(sf, feat, sizeof(double) * (size_t)n_sessions * n_windows * n_channels, st);
+    if (rc) return rc;
+    rc = stage_out(so, out, sizeof(double) * (size_t)n_sessions * n_rows * n_channels * (order + 1), st);
+    if (rc) { release(sf, st); return rc; }
+    rc = stack_run((const double*)sf.dev, (double*)so.dev, n_sessions, n_windows, n_channels, n_rows, first_row, order, step, st);
+    if (rc == SGS_OK) rc = finish_out(so, st);
+    const bool sync = so.host != nullptr;
+    release(sf, st);
+    release(so, st);
+    if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+}  // extern "C"

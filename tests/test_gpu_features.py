@@ -1,0 +1,97 @@
+"""CUDA feature extraction (through the C ABI) against the oracle and the reference-generated fixtures."""
+import numpy as np
+import pytest
+
+import oracle as O
+from sgs import synth
+from sgs.features import FeatureExtractor
+from helpers import load
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9      # absolute, on log-power values of magnitude ~5-12 (fp64 recurrences; FMA contraction differs from scipy)
+
+
+@pytest.mark.parametrize('sr', [1024, 2048])
+@pytest.mark.parametrize('ln', [50, 60])
+def test_offline_against_reference_fixture(sr, ln):
+    G = load('features.npz')
+    x = synth.seeg_session(7, 6, sr, 1.37)
+    fe = FeatureExtractor(sr, line_noise=ln)
+    lp = fe.log_power(x.astype(np.float64))
+    key = 'sr%d_ln%d' % (sr, ln)
+    assert lp.shape == G[key + '_offline_nostack'].shape
+    assert np.abs(lp - G[key + '_offline_nostack']).max() < TOL
+    st = fe.stack(lp)
+    assert st.shape == G[key + '_offline'].shape
+    assert np.abs(st - G[key + '_offline']).max() < TOL
+    # fp32 input path gives the same result (the synthetic data is exactly representable in fp32)
+    assert np.array_equal(fe.log_power(x), lp)
+
+
+@pytest.mark.parametrize('sr', [1024, 2048])
+@pytest.mark.parametrize('ln', [50, 60])
+def test_online_against_reference_fixture(sr, ln):
+    G = load('features.npz')
+    x = synth.seeg_session(7, 6, sr, 1.37)
+    fe = FeatureExtractor(sr, line_noise=ln, frame_len_ms=50, frame_shift_ms=10)
+    for cs, p in ((32, 16), (64, 64)):
+        g = G['sr%d_ln%d_online_cs%d_p%d' % (sr, ln, cs, p)]
+        st = fe.stack(fe.log_power(x, online=True, chunk_size=cs), online=True)
+        assert st.shape == g.shape
+        assert np.abs(st - g).max() < TOL
+
+
+def test_short_and_empty():
+    G = load('features.npz')
+    x = synth.seeg_session(8, 1, 1024, 0.30)
+    fe = FeatureExtractor(1024)
+    lp = fe.log_power(x)
+    assert np.abs(lp - G['short_offline_nostack']).max() < TOL
+    assert np.abs(fe.stack(lp) - G['short_offline']).max() < TOL
+    # fewer samples than one window -> no windows, no rows
+    tiny = fe.log_power(x[:30])
+    assert tiny.shape == (0, 1) and fe.stack(tiny).shape == (0, 5)
+
+
+@pytest.mark.parametrize('mode', ['exact', 'truncated', 'single'])
+def test_chunked_scan_matches_oracle(mode):
+    """Time-chunked scan: exact carry (Phi), truncated zero-state pass, and the un-chunked run agree with scipy."""
+    sr = 1024
+    x = synth.seeg_session(11, 5, sr, 60.0)
+    want = O.herff2016_b(x.astype(np.float64), sr, skip_stacking=True)
+    fe = FeatureExtractor(sr)
+    if mode == 'exact':
+        got = fe.log_power(x, chunks=30)                       # 2048-sample chunks << horizon -> Phi carry
+        assert fe.scan_plan(len(x), 5, 30)[3] is not None
+    elif mode == 'truncated':
+        got = fe.log_power(x, chunks=2)                        # 30720-sample chunks > horizon (23552)
+        assert fe.scan_plan(len(x), 5, 2)[3] is None and fe.scan_plan(len(x), 5, 2)[2] < 30720
+    else:
+        got = fe.log_power(x, chunks=1)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < TOL
+
+
+def test_many_sessions_ragged_channels():
+    """Session batch with a channel count that is not a multiple of the warp size."""
+    sr = 2048
+    xs = np.stack([synth.seeg_session(20 + s, 37, sr, 3.0) for s in range(3)])
+    fe = FeatureExtractor(sr)
+    got = fe.log_power(xs)
+    for s in range(3):
+        want = O.herff2016_b(xs[s].astype(np.float64), sr, skip_stacking=True)
+        assert np.abs(got[s] - want).max() < TOL
+
+
+def test_device_resident_tensors():
+    import torch
+    sr = 1024
+    x = synth.seeg_session(12, 16, sr, 5.0)
+    fe = FeatureExtractor(sr)
+    xd = torch.from_numpy(x).cuda()
+    lp = fe.log_power(xd)
+    assert lp.is_cuda
+    st = fe.stack(lp)
+    want = O.herff2016_b(x.astype(np.float64), sr)
+    assert np.abs(st.cpu().numpy() - want).max() < TOL
