@@ -1,12 +1,13 @@
 // C ABI for feature extraction (include/sgs.h).
+#include <math.h>
 #include <vector>
 #include "feat.cuh"
 #include "../../include/sgs.h"
 
 namespace sgs {
-int feat_run(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* carry, const double* phi,
+int feat_run(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* slots, const double* phi,
              bool apply_phi, const long long* bounds, const int* kfirst, const int* starts, const double* zf,
-             const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st);
+             const double* coef, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st);
 int stack_run(const double* feat, double* out, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,
               int order, int step, cudaStream_t st);
 }  // namespace sgs
@@ -17,6 +18,7 @@ struct sgs_feat_plan {
     int zero_fill = 0;
     sgs::FeatCoefs cf;
     double* d_zf = nullptr;               // zero-fill response table on the device
+    double* d_coef = nullptr;             // [n_biquads][5] on the device (per-lane register fill)
     // cached window table (re-uploaded only when the caller's table changes)
     std::vector<int32_t> h_starts;
     int32_t* d_starts = nullptr;
@@ -39,7 +41,10 @@ int sgs_feat_plan_create(sgs_feat_plan** plan, int n_filters, const double* coef
         for (int k = 0; k < 5; ++k) p->cf.c[i][k] = coef[i * 5 + k];
         p->cf.zi[i][0] = zi_unit[i * 2];
         p->cf.zi[i][1] = zi_unit[i * 2 + 1];
-        if (i % sgs::kSecPerFilter != 0 && !(coef[i * 5] == 1.0 && coef[i * 5 + 2] == 1.0)) monic = false;
+        // monic sections (b0 = b2 = 1) take the 4-flop form.  scipy's zpk2sos leaves b2 = 1 - 2^-52 on some
+        // notch sections (2048 Hz); a coefficient within 4 ulp of 1 is treated as 1 (documented in DESIGN.md).
+        const double ulp4 = 4 * 2.220446049250313e-16;
+        if (i % sgs::kSecPerFilter != 0 && !(fabs(coef[i * 5] - 1.0) <= ulp4 && fabs(coef[i * 5 + 2] - 1.0) <= ulp4)) monic = false;
     }
     p->monic = monic;
     for (int s = 0; s < sgs::kSecPerFilter; ++s) {
@@ -51,6 +56,11 @@ int sgs_feat_plan_create(sgs_feat_plan** plan, int n_filters, const double* coef
         if (e == cudaSuccess) e = cudaMemcpy(p->d_zf, zero_fill_response, sizeof(double) * zero_fill, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { delete p; return sgs::cuda_fail(e, "zero-fill table upload", __FILE__, __LINE__); }
     }
+    {
+        cudaError_t e = cudaMalloc(&p->d_coef, sizeof(double) * 5 * p->n_biquads);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_coef, coef, sizeof(double) * 5 * p->n_biquads, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { sgs_feat_plan_destroy(p); return sgs::cuda_fail(e, "coefficient upload", __FILE__, __LINE__); }
+    }
     *plan = p;
     return SGS_OK;
 }
@@ -58,6 +68,7 @@ int sgs_feat_plan_create(sgs_feat_plan** plan, int n_filters, const double* coef
 void sgs_feat_plan_destroy(sgs_feat_plan* p) {
     if (!p) return;
     if (p->d_zf) cudaFree(p->d_zf);
+    if (p->d_coef) cudaFree(p->d_coef);
     if (p->d_starts) cudaFree(p->d_starts);
     delete p;
 }
@@ -81,8 +92,6 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
     // validate the window table on the host (it is O(frames), tiny next to the sample data)
     for (int k = 0; k < n_windows; ++k) {
         SGS_ARG(k == 0 || win_starts[k] > win_starts[k - 1], "win_starts must be strictly increasing (k=%d)", k);
-        SGS_ARG(k + kFifo >= n_windows || win_starts[k + kFifo] >= win_starts[k] + window_len,
-                "more than %d windows open at once (k=%d)", kFifo, k);
     }
     SGS_ARG(win_starts[0] >= -p->zero_fill, "first window starts before the zero-fill region");
     SGS_ARG((int64_t)win_starts[n_windows - 1] + window_len <= n_samples, "last window ends past the input");
@@ -141,7 +150,7 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
     // small per-call tables + carry scratch, stream-ordered
     const int ns = 2 * p->n_biquads;
     const size_t tab_bytes = sizeof(long long) * (n_chunks + 1) + sizeof(int) * (n_chunks + 1) + (apply_phi ? sizeof(double) * ns * ns : 0);
-    const size_t carry_bytes = n_chunks > 1 ? sizeof(double) * (size_t)(n_chunks - 1) * ns * g.n_streams : 0;
+    const size_t carry_bytes = sizeof(double) * (size_t)n_chunks * ns * g.n_streams;      // state slot per chunk start
     char* d_tab = nullptr;
     double* d_carry = nullptr;
     std::vector<char> h_tab(tab_bytes);
@@ -158,7 +167,7 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
     // the pageable h_tab copy above is staged synchronously by the runtime, so h_tab may go out of scope
 
     rc = feat_run(p->n_biquads, p->monic, sx.dev, x_is_f64 != 0, (double*)sf.dev, d_carry, (const double*)(d_tab + off_phi),
-                  apply_phi, (const long long*)d_tab, (const int*)(d_tab + off_k), p->d_starts, p->d_zf, p->cf, g, st);
+                  apply_phi, (const long long*)d_tab, (const int*)(d_tab + off_k), p->d_starts, p->d_zf, p->d_coef, p->cf, g, st);
     if (rc == SGS_OK) rc = finish_out(sf, st);
     cudaFreeAsync(d_tab, st);
     if (d_carry) cudaFreeAsync(d_carry, st);

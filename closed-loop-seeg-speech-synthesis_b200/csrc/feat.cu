@@ -2,147 +2,274 @@
 //
 // Data layout in HBM
 //   x      [session][t][channel]   fp32 or fp64, time-major exactly as the reference hands it over
-//                                  (samples x channels); a warp = 32 consecutive channels of one
-//                                  sample = one 128 B line (fp32) -> coalesced, one line per warp-load.
+//                                  (samples x channels)
 //   feat   [session][window][channel]  fp64 log-power, un-stacked (the stacked view is a gather)
-//   carry  [chunk][state][stream]  fp64, stream = session*C + channel (coalesced over streams)
+//   state  [chunk][state][stream]  fp64, stream = session*C + channel; slot j = cascade state at the
+//                                  START of time chunk j (slot 0 = the reference's cold/warm start)
 //
-// Parallel decomposition: one thread = one stream (session, channel) x one time chunk.  The 24-biquad
-// cascade is a 48-state linear recurrence; chunks are made independent by an exact scan:
-//   pass 1 (k_iir_state)  zero-state run over the last `horizon` samples of each chunk -> end state e_j
-//   carry  (k_iir_carry)  s_{j+1} = Phi(L) s_j + e_j   (only when horizon >= L, i.e. Phi(L) not negligible)
-//   pass 2 (k_iir_feat)   re-run each chunk from its true initial state, fused with window energy + log
+// Parallel decomposition (k_iir_stages): a CTA is 4 warps = 4 pipeline stages of the cascade (6 biquads
+// each) for 32 streams (lane = stream).  Stage w consumes the 16-sample batch stage w-1 produced in the
+// previous iteration through a double-buffered shared-memory hand-off; one bar.sync per iteration.
+// Why stages across warps: with warp-uniform roles every coefficient is a uniform-register operand.
+// Measured on B200 (tools/pipe_peak.cu): DFMA with three distinct 64-bit register operands issues every
+// 3 cycles (12.3 T/s), with a uniform operand every 2 (18.5 T/s); a thread that owns all 24 sections needs
+// 78 coefficient doubles and stalls on LDCU re-loads (first version: 37 % of the pipe), and a lane-systolic
+// version with per-lane coefficient registers is capped by the register-file limit (second version: 50 %).
+// Stage 0 reads the input coalesced (32 consecutive channels of one sample = 128 B per warp load), one
+// batch ahead; the last stage keeps a prefix-sum ring of y^2 and closes windows once per batch.
+//
+// Time is cut into chunks that are made independent by an exact scan over the 48-state recurrence:
+//   k_iir_init    slot 0 = state before the first sample (cold start on x[0], offline.py:51-62)
+//   pass 1        k_iir_stages<STATE>: zero-state run over the last `horizon` samples of chunk j -> slot j+1
+//   k_iir_carry   slot j+1 = Phi(L) slot j + e_j   (only when horizon >= L, i.e. Phi(L) is not negligible)
+//   pass 2        k_iir_stages<FEAT>: re-run each chunk from its slot, fused with window energy + log
 // `horizon` is chosen on the host from the actual transition matrix so that |A^horizon| is below the
-// requested tolerance (default 2^-70, far under one fp64 ulp of the state), see sgs/design.py.
+// requested tolerance (default 2^-70, far under one fp64 ulp of the state), see sgs/features.py.
 #include "feat.cuh"
 
 namespace sgs {
 
-template <typename T> __device__ __forceinline__ double ld_in(const T* p) { return (double)__ldg(p); }
+template <typename T> __device__ __forceinline__ float ld_f(const T* p) { return (float)__ldg(p); }
+template <typename T> __device__ __forceinline__ double ld_d(const T* p) { return (double)__ldg(p); }
 
-// One sample through `NB` biquads.  Sections 0, 8, 16 carry the filter gain (general form, 5 flops);
-// all others are monic (b0 = b2 = 1, verified on the host) and need 4.
-template <int NB, bool MONIC>
-__device__ __forceinline__ double cascade(double v, double (&z)[NB][2], const FeatCoefs& cf) {
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        double y;
-        if (MONIC && (i % kSecPerFilter) != 0) {
-            y = v + z[i][0];
-            z[i][0] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z[i][1]));
-            z[i][1] = fma(-cf.c[i][4], y, v);
-        } else {
-            y = fma(cf.c[i][0], v, z[i][0]);
-            z[i][0] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z[i][1]));
-            z[i][1] = fma(-cf.c[i][4], y, cf.c[i][2] * v);
-        }
-        v = y;
-    }
-    return v;
-}
-
-// Cold start on the first sample of a session (offline.py:51-66 / FrameBuffer.py:87-92):
-// filter 0 state = zi * x[0]; middle filters = zi * (previous filter's first output);
-// last filter = its warm-started state.  Processes sample 0 and returns its output.
-template <int NB, bool MONIC>
-__device__ __forceinline__ double cold_start(double x0, double (&z)[NB][2], const FeatCoefs& cf) {
-    constexpr int NF = NB / kSecPerFilter;
-    double v = x0;
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-#pragma unroll
-        for (int s = 0; s < kSecPerFilter; ++s) {
-            const int i = f * kSecPerFilter + s;
-            if (f == NF - 1) {
-                z[i][0] = cf.zi_warm[s][0];
-                z[i][1] = cf.zi_warm[s][1];
-            } else {
-                z[i][0] = cf.zi[i][0] * v;     // v is x[0] for f == 0, the filtered first sample after
-                z[i][1] = cf.zi[i][1] * v;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < kSecPerFilter; ++s) {
-            const int i = f * kSecPerFilter + s;
-            double y;
-            if (MONIC && s != 0) {
-                y = v + z[i][0];
-                z[i][0] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z[i][1]));
-                z[i][1] = fma(-cf.c[i][4], y, v);
-            } else {
-                y = fma(cf.c[i][0], v, z[i][0]);
-                z[i][0] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z[i][1]));
-                z[i][1] = fma(-cf.c[i][4], y, cf.c[i][2] * v);
-            }
-            v = y;
-        }
-    }
-    return v;
-}
-
-constexpr int kUnroll = 8;          // samples fetched ahead per thread (software pipeline over HBM latency)
 constexpr int kThreads = 128;
 
 // ------------------------------------------------------------------------------------------------
-// pass 1: end state of chunk j from a zero-state (or, at t = 0, the true cold-start) run over its
-// last `horizon` samples.  grid = (streams/128, n_chunks-1)
+// slot 0: the state the reference starts from (local/offline.py:39-62, FrameBuffer.py:87-98):
+// filter 0: zi * x[0]; middle filter(s): zi * (first output of the previous filter); last: warm state.
 // ------------------------------------------------------------------------------------------------
-template <int NB, bool MONIC, typename TIn>
-__global__ void __launch_bounds__(kThreads)
-k_iir_state(const TIn* __restrict__ x, double* __restrict__ carry, const long long* __restrict__ bounds,
-            const __grid_constant__ FeatCoefs cf, const __grid_constant__ FeatGeom g) {
-    const int stream = blockIdx.x * kThreads + threadIdx.x;
-    const int j = blockIdx.y;
+template <int NB, typename TIn>
+__global__ void k_iir_init(const TIn* __restrict__ x, double* __restrict__ state,
+                           const __grid_constant__ FeatCoefs cf, const __grid_constant__ FeatGeom g) {
+    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
     if (stream >= g.n_streams) return;
+    constexpr int NF = NB / kSecPerFilter;
     const int sess = stream / g.n_channels, ch = stream - sess * g.n_channels;
-    const TIn* xp = x + (long long)sess * g.session_stride + ch;
-    const long long t_end = bounds[j + 1];
-    long long t = bounds[j];
-    if (t_end - g.horizon > t) t = t_end - g.horizon;
+    double v = ld_d(x + (long long)sess * g.session_stride + ch);
+    double* out = state + stream;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        double z0[kSecPerFilter], z1[kSecPerFilter];
+#pragma unroll
+        for (int s = 0; s < kSecPerFilter; ++s) {
+            const int i = f * kSecPerFilter + s;
+            z0[s] = (f == NF - 1) ? cf.zi_warm[s][0] : cf.zi[i][0] * v;
+            z1[s] = (f == NF - 1) ? cf.zi_warm[s][1] : cf.zi[i][1] * v;
+            out[(long long)(2 * i) * g.state_stride] = z0[s];
+            out[(long long)(2 * i + 1) * g.state_stride] = z1[s];
+        }
+        // first output of this filter (state left untouched: the main kernel processes sample 0 again)
+#pragma unroll
+        for (int s = 0; s < kSecPerFilter; ++s) v = fma(cf.c[f * kSecPerFilter + s][0], v, z0[s]);
+    }
+}
 
-    double z[NB][2];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) z[i][0] = z[i][1] = 0.0;
-    if (t == 0) {                                   // chunk 0 seen from its beginning: exact cold start
-        cold_start<NB, MONIC>(ld_in(xp), z, cf);
-        t = 1;
-    }
+enum { kModeState = 0, kModeFeat = 1 };
+
+constexpr int kStages = 4;                      // warps per CTA = pipeline stages of the cascade
+constexpr int kBatch = 16;                      // samples handed from stage to stage per iteration
+constexpr int kStreamsPerBlock = 32;            // lane = stream
+
+__device__ __forceinline__ void block_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// One pipeline stage = BPS consecutive biquads of the cascade, run by one warp for 32 streams.
+// Coefficients are compile-time offsets into the __grid_constant__ parameter block, so they reach the
+// FP64 pipe as uniform-register / constant operands: a DFMA with three distinct 64-bit REGISTER operands
+// only issues every 3 cycles on sm_100 (measured, tools/pipe_peak.cu), with a uniform operand every 2.
+template <int NB, bool MONIC, int MODE, int RING, int STAGE, typename TIn>
+__device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __restrict__ feat,
+                                          double* __restrict__ state, const int* __restrict__ starts,
+                                          const double* __restrict__ zero_fill_resp, const FeatCoefs& cf,
+                                          const FeatGeom& g, double* __restrict__ smem, const int j,
+                                          const long long t_begin, const int len, const int k_lo, const int k_hi) {
+    constexpr int BPS = NB / kStages, FIRST = STAGE * BPS;
+    constexpr bool LAST = STAGE == kStages - 1;
+    const int lane = threadIdx.x & 31;
+    int stream = blockIdx.x * kStreamsPerBlock + lane;
+    const bool live = stream < g.n_streams;
+    if (!live) stream = g.n_streams - 1;
+    const int sess = stream / g.n_channels, ch = stream - sess * g.n_channels;
     const long long C = g.n_channels;
-    double buf[kUnroll];
+
+    // stage hand-off buffers: buf[s][parity][kBatch][32] (output of stage s), then the prefix ring (FEAT)
+    double* buf_out = smem + (size_t)STAGE * 2 * kBatch * 32;
+    const double* buf_in = smem + (size_t)(STAGE > 0 ? STAGE - 1 : 0) * 2 * kBatch * 32;
+    double* ring = smem + (size_t)(kStages - 1) * 2 * kBatch * 32;         // [RING][32]
+
+    // state of this stage's sections for this lane's stream
+    double z0[BPS], z1[BPS];
+    {
+        const bool zero_state = (MODE == kModeState) && (j > 0 || t_begin != 0 /*truncated*/);
+        const double* sp = state + ((long long)j * (2 * NB)) * g.state_stride + stream;
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) buf[u] = (t + u < t_end) ? ld_in(xp + (t + u) * C) : 0.0;
-    for (; t < t_end; t += kUnroll) {
-        double nxt[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) nxt[u] = (t + kUnroll + u < t_end) ? ld_in(xp + (t + kUnroll + u) * C) : 0.0;
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (t + u < t_end) cascade<NB, MONIC>(buf[u], z, cf);
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) buf[u] = nxt[u];
+        for (int p = 0; p < BPS; ++p) {
+            const int i = FIRST + p;
+            z0[p] = zero_state ? 0.0 : sp[(long long)(2 * i) * g.state_stride];
+            z1[p] = zero_state ? 0.0 : sp[(long long)(2 * i + 1) * g.state_stride];
+        }
     }
-    double* out = carry + ((long long)j * (2 * NB)) * g.state_stride + stream;
+
+    // stage 0: input prefetch, one batch ahead, coalesced (32 consecutive channels of one sample per warp load)
+    const TIn* xrow = x + (long long)sess * g.session_stride + ch + t_begin * C;
+    const long long t_last = g.n_samples - 1 - t_begin;                    // clamp: never read past the session
+    float xq[STAGE == 0 ? kBatch : 1];
+    if (STAGE == 0) {
 #pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        out[(long long)(2 * i) * g.state_stride] = z[i][0];
-        out[(long long)(2 * i + 1) * g.state_stride] = z[i][1];
+        for (int u = 0; u < kBatch; ++u) xq[u] = ld_f(xrow + (long long)(u < t_last ? u : t_last) * C);
+    }
+
+    // last stage: prefix-sum ring + window closing (see k_iir_stages header)
+    constexpr int kRebase = 4096;
+    double P = 0.0;
+    int ke = k_lo, next_end = 0x7fffffff, after_end = 0x7fffffff, rebase_m = -0x40000000, zf_lo = 0;
+    double rebase_off = 0.0;
+    double* fp = feat + ((long long)sess * g.n_windows) * C + ch;
+    if (LAST && MODE == kModeFeat) {
+        next_end = (int)((long long)starts[k_lo] + g.window_len - t_begin);
+        if (k_lo + 1 < k_hi) after_end = (int)((long long)starts[k_lo + 1] + g.window_len - t_begin);
+        if (j == 0 && g.t_first < 0) {
+            // online framing starts inside the warm-start zero fill of the last filter (FrameBuffer.py:95-98): its
+            // response there is a session-independent table; seed the ring with its prefix sums
+            zf_lo = g.t_first;
+            for (int t = g.t_first; t < 0; ++t) {
+                const double r = zero_fill_resp[t + g.zero_fill];
+                P = fma(r, r, P);
+                ring[(t & (RING - 1)) * 32 + lane] = P;
+            }
+        }
+    }
+
+    const int n_batches = (len + kBatch - 1) / kBatch;
+    for (int it = 0; it < n_batches + kStages - 1; ++it) {
+        const int bidx = it - STAGE;
+        if (bidx >= 0 && bidx < n_batches) {
+            const int m0 = bidx * kBatch;                                  // first sample (relative) of this batch
+            float xn[STAGE == 0 ? kBatch : 1];
+            if (STAGE == 0) {
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const long long m = (long long)m0 + kBatch + u;
+                    xn[u] = ld_f(xrow + (m < t_last ? m : t_last) * C);
+                }
+            }
+            const double* in = buf_in + (size_t)((it - 1) & 1) * kBatch * 32 + lane;
+            double* out = buf_out + (size_t)(it & 1) * kBatch * 32 + lane;
+            // two half-batches of 8 samples: keeps every stage's loop body (~300 instructions) inside the
+            // per-scheduler instruction cache while the 4 warps of a CTA execute 4 different bodies
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int uu = 0; uu < kBatch / 2; ++uu) {
+                    const int u = h * (kBatch / 2) + uu;
+                    double v = (STAGE == 0) ? (double)(h == 0 ? xq[uu] : xq[uu + kBatch / 2]) : in[u * 32];
+#pragma unroll
+                    for (int p = 0; p < BPS; ++p) {
+                        const int i = FIRST + p;
+                        double y;
+                        if (MONIC && (i % kSecPerFilter) != 0) {
+                            y = v + z0[p];
+                            z0[p] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z1[p]));
+                            z1[p] = fma(-cf.c[i][4], y, v);
+                        } else {
+                            y = fma(cf.c[i][0], v, z0[p]);
+                            z0[p] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z1[p]));
+                            z1[p] = fma(-cf.c[i][4], y, cf.c[i][2] * v);
+                        }
+                        v = y;
+                    }
+                    if (!LAST) out[u * 32] = v;
+                    else if (MODE == kModeFeat) {
+                        P = fma(v, v, P);
+                        ring[((m0 + u) & (RING - 1)) * 32 + lane] = P;
+                    }
+                }
+            }
+            if (STAGE == 0) {
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) xq[u] = xn[u];
+            }
+            if (LAST && MODE == kModeFeat) {
+                const int done = m0 + kBatch;                              // samples [0, done) have their prefix in the ring
+                while (next_end <= done) {
+                    const int e = next_end, s0 = e - g.window_len;
+                    double hi = ring[((e - 1) & (RING - 1)) * 32 + lane];
+                    const double lo = (s0 - 1 < zf_lo) ? 0.0 : ring[((s0 - 1) & (RING - 1)) * 32 + lane];
+                    if (s0 - 1 < rebase_m && e - 1 >= rebase_m) hi += rebase_off;      // window straddles the last re-base
+                    if (live) fp[(long long)ke * C] = log((hi - lo) + 0.01);
+                    ++ke;
+                    next_end = after_end;
+                    after_end = (ke + 1 < k_hi) ? (int)((long long)starts[ke + 1] + g.window_len - t_begin) : 0x7fffffff;
+                }
+                if (done - rebase_m >= kRebase) {
+                    // P restarts from 0 so that hi - lo never cancels more than ~kRebase/window_len ulps
+                    rebase_m = done;
+                    rebase_off = P;
+                    P = 0.0;
+                }
+            }
+        }
+        block_sync();
+    }
+
+    if (MODE == kModeState && live) {
+        double* outp = state + ((long long)(j + 1) * (2 * NB)) * g.state_stride + stream;
+#pragma unroll
+        for (int p = 0; p < BPS; ++p) {
+            const int i = FIRST + p;
+            outp[(long long)(2 * i) * g.state_stride] = z0[p];
+            outp[(long long)(2 * i + 1) * g.state_stride] = z1[p];
+        }
+    }
+}
+
+// grid = (ceil(streams/32), chunks); block = 4 warps = 4 pipeline stages.
+// FEAT mode: the last stage keeps a running prefix sum P of y^2 per stream and writes it to a ring in shared
+// memory (slot = sample index & (RING-1)); a window [s, e) is P[e-1] - P[s-1], closed once per batch, all 32
+// streams of the warp at once (coalesced 256 B store of the log-power row segment).
+template <int NB, bool MONIC, int MODE, int RING, typename TIn>
+__global__ void __launch_bounds__(kStages * 32)
+k_iir_stages(const TIn* __restrict__ x, double* __restrict__ feat, double* __restrict__ state,
+             const long long* __restrict__ bounds, const int* __restrict__ kfirst, const int* __restrict__ starts,
+             const double* __restrict__ zero_fill_resp, const __grid_constant__ FeatCoefs cf,
+             const __grid_constant__ FeatGeom g) {
+    extern __shared__ double smem[];
+    const int j = blockIdx.y;
+    long long t_begin = bounds[j], t_end;
+    int k_lo = 0, k_hi = 0;
+    if (MODE == kModeState) {
+        t_end = bounds[j + 1];
+        if (t_end - g.horizon > t_begin) t_begin = t_end - g.horizon;      // truncated zero-state pass
+    } else {
+        k_lo = kfirst[j]; k_hi = kfirst[j + 1];
+        if (k_lo >= k_hi) return;
+        t_end = (long long)starts[k_hi - 1] + g.window_len;                // run on until the last owned window closes
+    }
+    const int len = (int)(t_end - t_begin);
+    // in STATE mode the host guarantees len % kBatch == 0 so that the end state is taken exactly at t_end
+    // rotate the stage -> warp (= scheduler) assignment with the block index so that co-resident CTAs do not
+    // stack all their heaviest stages on the same scheduler
+    switch (((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & (kStages - 1)) {
+        case 0: run_stage<NB, MONIC, MODE, RING, 0, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
+        case 1: run_stage<NB, MONIC, MODE, RING, 1, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
+        case 2: run_stage<NB, MONIC, MODE, RING, 2, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
+        default: run_stage<NB, MONIC, MODE, RING, 3, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// carry: s_{j+1} = Phi s_j + e_j over the equal-length interior chunks (in place).  One thread per
-// stream; Phi (NS x NS, row-major) is read warp-uniformly.
+// carry (exact mode): slot j+1 = Phi slot j + e_j for j >= 1, in place; slot 1 is already the true state
+// (chunk 0 ran from slot 0).  One thread per stream; Phi (NS x NS, row-major) is read warp-uniformly.
 // ------------------------------------------------------------------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(kThreads)
-k_iir_carry(double* __restrict__ carry, const double* __restrict__ phi, int n_states_chunks, int n_streams) {
+k_iir_carry(double* __restrict__ slots, const double* __restrict__ phi, int n_chunks, int n_streams) {
     const int stream = blockIdx.x * kThreads + threadIdx.x;
     if (stream >= n_streams) return;
     double s[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) s[i] = carry[(long long)i * n_streams + stream];
-    for (int j = 1; j < n_states_chunks; ++j) {
-        double* e = carry + (long long)j * NS * n_streams + stream;
+    for (int i = 0; i < NS; ++i) s[i] = slots[((long long)NS + i) * n_streams + stream];      // slot 1
+    for (int j = 2; j < n_chunks; ++j) {
+        double* e = slots + (long long)j * NS * n_streams + stream;
         double r[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) r[i] = e[(long long)i * n_streams];
@@ -158,88 +285,6 @@ k_iir_carry(double* __restrict__ carry, const double* __restrict__ phi, int n_st
             s[i] = r[i];
             e[(long long)i * n_streams] = r[i];
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// pass 2: filter each chunk from its true initial state and emit log window energies.
-// Chunk j owns the windows whose START lies in [bounds[j], bounds[j+1]) and runs on past its end
-// until the last owned window closes (window_len - 1 samples of overlap at most).
-// grid = (streams/128, n_chunks)
-// ------------------------------------------------------------------------------------------------
-template <int NB, bool MONIC, typename TIn>
-__global__ void __launch_bounds__(kThreads)
-k_iir_feat(const TIn* __restrict__ x, double* __restrict__ feat, const double* __restrict__ carry,
-           const long long* __restrict__ bounds, const int* __restrict__ kfirst,
-           const int* __restrict__ starts, const double* __restrict__ zero_fill_resp,
-           const __grid_constant__ FeatCoefs cf, const __grid_constant__ FeatGeom g) {
-    __shared__ double ring[kFifo][kThreads];
-    const int stream = blockIdx.x * kThreads + threadIdx.x;
-    const int j = blockIdx.y;
-    const int k_lo = kfirst[j], k_hi = kfirst[j + 1];
-    if (stream >= g.n_streams || k_lo >= k_hi) return;
-    const int sess = stream / g.n_channels, ch = stream - sess * g.n_channels;
-    const TIn* xp = x + (long long)sess * g.session_stride + ch;
-    double* fp = feat + ((long long)sess * g.n_windows) * g.n_channels + ch;
-    const long long C = g.n_channels;
-    const int wl = g.window_len;
-    const long long t_stop = (long long)starts[k_hi - 1] + wl;       // exclusive; host guarantees <= n_samples
-
-    // window bookkeeping (uniform across the block: every thread sits at the same t)
-    int ks = k_lo, ke = k_lo;
-    long long next_start = starts[ks];
-    long long after_start = (ks + 1 < k_hi) ? starts[ks + 1] : (1LL << 62);
-    long long next_end = next_start + wl;
-    double P = 0.0;
-    auto account = [&](long long t, double y) {
-        if (t == next_start) {
-            if (ks > k_lo) ring[(ks - 1) & (kFifo - 1)][threadIdx.x] = P;   // segment [s_{ks-1}, s_ks) closed
-            P = 0.0;
-            ++ks;
-            next_start = after_start;
-            after_start = (ks + 1 < k_hi) ? starts[ks + 1] : (1LL << 62);
-        }
-        P = fma(y, y, P);
-        if (t + 1 == next_end) {
-            double acc = 0.0;
-            for (int i = ke; i < ks - 1; ++i) acc += ring[i & (kFifo - 1)][threadIdx.x];
-            acc += P;
-            fp[(long long)ke * C] = log(acc + 0.01);
-            ++ke;
-            next_end = (ke < k_hi) ? (long long)starts[ke] + wl : (1LL << 62);
-        }
-    };
-
-    double z[NB][2];
-    long long t;
-    if (j == 0) {
-        // online framing starts inside the warm-start zero fill of the last filter: its response there
-        // is a session-independent constant table (FrameBuffer.py:95-98)
-        for (t = g.t_first; t < 0; ++t) account(t, zero_fill_resp[t + g.zero_fill]);
-        const double y0 = cold_start<NB, MONIC>(ld_in(xp), z, cf);
-        account(0, y0);
-        t = 1;
-    } else {
-        const double* sp = carry + ((long long)(j - 1) * (2 * NB)) * g.state_stride + stream;
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            z[i][0] = sp[(long long)(2 * i) * g.state_stride];
-            z[i][1] = sp[(long long)(2 * i + 1) * g.state_stride];
-        }
-        t = bounds[j];
-    }
-    double buf[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) buf[u] = (t + u < t_stop) ? ld_in(xp + (t + u) * C) : 0.0;
-    for (; t < t_stop; t += kUnroll) {
-        double nxt[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) nxt[u] = (t + kUnroll + u < t_stop) ? ld_in(xp + (t + kUnroll + u) * C) : 0.0;
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (t + u < t_stop) account(t + u, cascade<NB, MONIC>(buf[u], z, cf));
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) buf[u] = nxt[u];
     }
 }
 
@@ -264,56 +309,65 @@ __global__ void k_stack(const double* __restrict__ feat, double* __restrict__ ou
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-template <int NB, bool MONIC, typename TIn>
-static void launch_state(const TIn* x, double* carry, const long long* bounds, const FeatCoefs& cf, const FeatGeom& g,
-                         cudaStream_t st) {
-    dim3 grid(ceil_div(g.n_streams, kThreads), g.n_chunks - 1);
-    k_iir_state<NB, MONIC, TIn><<<grid, kThreads, 0, st>>>(x, carry, bounds, cf, g);
+template <int NB, bool MONIC, int RING, typename TIn>
+static void run_all(const TIn* x, double* feat, double* slots, const double* phi, bool apply_phi, const long long* bounds,
+                    const int* kfirst, const int* starts, const double* zf, const FeatCoefs& cf, const FeatGeom& g,
+                    cudaStream_t st) {
+    k_iir_init<NB, TIn><<<ceil_div(g.n_streams, 128), 128, 0, st>>>(x, slots, cf, g);
     SGS_LAUNCHED();
-}
-
-template <int NB, bool MONIC, typename TIn>
-static void launch_feat(const TIn* x, double* feat, const double* carry, const long long* bounds, const int* kfirst,
-                        const int* starts, const double* zf, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
-    dim3 grid(ceil_div(g.n_streams, kThreads), g.n_chunks);
-    k_iir_feat<NB, MONIC, TIn><<<grid, kThreads, 0, st>>>(x, feat, carry, bounds, kfirst, starts, zf, cf, g);
+    const int bx = ceil_div(g.n_streams, kStreamsPerBlock);
+    constexpr int hand_bytes = (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
+    constexpr int feat_bytes = hand_bytes + RING * 32 * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_iir_stages<NB, MONIC, kModeFeat, RING, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, feat_bytes);
+        attr_set = true;
+    }
+    if (g.n_chunks > 1) {
+        k_iir_stages<NB, MONIC, kModeState, RING, TIn><<<dim3(bx, g.n_chunks - 1), kStages * 32, hand_bytes, st>>>(
+            x, feat, slots, bounds, kfirst, starts, zf, cf, g);
+        SGS_LAUNCHED();
+        if (apply_phi && g.n_chunks > 2) {
+            k_iir_carry<2 * NB><<<ceil_div(g.n_streams, kThreads), kThreads, 0, st>>>(slots, phi, g.n_chunks, g.n_streams);
+            SGS_LAUNCHED();
+        }
+    }
+    k_iir_stages<NB, MONIC, kModeFeat, RING, TIn><<<dim3(bx, g.n_chunks), kStages * 32, feat_bytes, st>>>(
+        x, feat, slots, bounds, kfirst, starts, zf, cf, g);
     SGS_LAUNCHED();
 }
 
 template <typename TIn>
-static int run_typed(int n_biquads, bool monic, const TIn* x, double* feat, double* carry, const double* phi,
+static int run_typed(int n_biquads, bool monic, const TIn* x, double* feat, double* slots, const double* phi,
                      bool apply_phi, const long long* bounds, const int* kfirst, const int* starts, const double* zf,
-                     const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
-#define SGS_DISPATCH(NB, M)                                                                         \
-    do {                                                                                            \
-        if (g.n_chunks > 1) {                                                                       \
-            launch_state<NB, M, TIn>(x, carry, bounds, cf, g, st);                                  \
-            if (apply_phi && g.n_chunks > 2) {                                                      \
-                k_iir_carry<2 * NB><<<ceil_div(g.n_streams, kThreads), kThreads, 0, st>>>(          \
-                    carry, phi, g.n_chunks - 1, g.n_streams);                                       \
-                SGS_LAUNCHED();                                                                     \
-            }                                                                                       \
-        }                                                                                           \
-        launch_feat<NB, M, TIn>(x, feat, carry, bounds, kfirst, starts, zf, cf, g, st);             \
+                     const double* coef, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
+    (void)coef;
+#define SGS_RUN(NB, M, RING) run_all<NB, M, RING, TIn>(x, feat, slots, phi, apply_phi, bounds, kfirst, starts, zf, cf, g, st)
+#define SGS_PICK(NB, M)                                             \
+    do {                                                            \
+        if (g.window_len + kBatch + 1 <= 128) SGS_RUN(NB, M, 128);  \
+        else SGS_RUN(NB, M, 256);                                   \
     } while (0)
-    if (n_biquads == 24 && monic) SGS_DISPATCH(24, true);
-    else if (n_biquads == 24) SGS_DISPATCH(24, false);
-    else if (n_biquads == 16 && monic) SGS_DISPATCH(16, true);
-    else if (n_biquads == 16) SGS_DISPATCH(16, false);
+    if (g.window_len + kBatch + 1 > 256) { set_error("window_len %d too long (max %d)", g.window_len, 255 - kBatch); return SGS_ERR_UNSUPPORTED; }
+    if (n_biquads == 24 && monic) SGS_PICK(24, true);
+    else if (n_biquads == 24) SGS_PICK(24, false);
+    else if (n_biquads == 16 && monic) SGS_PICK(16, true);
+    else if (n_biquads == 16) SGS_PICK(16, false);
     else { set_error("unsupported biquad count %d (16 or 24)", n_biquads); return SGS_ERR_UNSUPPORTED; }
-#undef SGS_DISPATCH
+#undef SGS_PICK
+#undef SGS_RUN
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;
 }
 
-int feat_run(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* carry, const double* phi,
+int feat_run(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* slots, const double* phi,
              bool apply_phi, const long long* bounds, const int* kfirst, const int* starts, const double* zf,
-             const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
+             const double* coef, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
     if (x_is_f64)
-        return run_typed<double>(n_biquads, monic, (const double*)x, feat, carry, phi, apply_phi, bounds, kfirst, starts,
-                                 zf, cf, g, st);
-    return run_typed<float>(n_biquads, monic, (const float*)x, feat, carry, phi, apply_phi, bounds, kfirst, starts, zf,
-                            cf, g, st);
+        return run_typed<double>(n_biquads, monic, (const double*)x, feat, slots, phi, apply_phi, bounds, kfirst, starts,
+                                 zf, coef, cf, g, st);
+    return run_typed<float>(n_biquads, monic, (const float*)x, feat, slots, phi, apply_phi, bounds, kfirst, starts, zf,
+                            coef, cf, g, st);
 }
 
 int stack_run(const double* feat, double* out, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,

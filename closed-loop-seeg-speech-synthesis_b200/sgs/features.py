@@ -12,7 +12,8 @@ from . import _lib
 from .design import FeaturePlan
 
 SM_COUNT = 148
-THREADS_PER_SM = 384            # k_iir_feat needs 168 registers -> 3 warps per scheduler
+STREAMS_PER_BLOCK = 32          # csrc/feat.cu: one CTA = 4 stage-warps x 32 streams
+BLOCKS_PER_SM = 3               # co-resident CTAs needed to cover the hand-off latency (measured optimum)
 MIN_CHUNK = 2048                # amortises the window overlap (<= 102 samples) and the carry step
 DEFAULT_TOL = 2.0 ** -70
 
@@ -94,7 +95,8 @@ class FeatureExtractor:
         """(n_chunks, chunk_len, horizon, phi-or-None)."""
         chunks = chunks if chunks is not None else os.environ.get('SGS_FEAT_CHUNKS')
         if chunks is None:
-            want = -(-SM_COUNT * THREADS_PER_SM // max(1, n_streams))
+            groups = -(-n_streams // STREAMS_PER_BLOCK)
+            want = max(1, int(round(SM_COUNT * BLOCKS_PER_SM / groups)))
             chunks = max(1, min(want, n_samples // MIN_CHUNK))
         chunks = int(chunks)
         if chunks <= 1:
