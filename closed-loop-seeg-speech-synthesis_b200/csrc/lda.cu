@@ -1,0 +1,117 @@
+// Per-mel-bin LDA decoding fused with dequantisation and the 5-tap smoothing.
+//
+// Reference semantics restated (paths under the reference tree):
+//   livenodes/LDASynthesis.py:19-28   per bin: scores = x[select] . coef_^T + intercept_; label = classes_[argmax]
+//                                     (sklearn: first maximum wins; binary estimators: single score > 0)
+//   livenodes/Dequantization.py:15-18 spec = medians[bin, label] then scipy.ndimage.gaussian_filter(sigma=0.5)
+//                                     across the bins, mode 'reflect' (the batch helper quantization.py:125-135
+//                                     does not smooth)
+//
+// FP64 CUDA-core kernel.  The stacked feature vector of a frame is never materialised: feature f of row r is
+// gathered straight from the un-stacked log-power array, feat[r + first_row - (order - tap)*step][c] with
+// (c, tap) = divmod(select[f], order + 1), exact zero before the stream start.
+//
+// Layout: W is repacked on upload to [bin][feature][class] so that the 9 class weights of one (bin, feature)
+// are contiguous and warp-uniform.  Block = 4 warps x 32 frames (lane = frame); warp w scores bins w, w+4, ...
+#include <math.h>
+#include "common.cuh"
+
+namespace sgs {
+
+constexpr int kLdaFrames = 32;
+constexpr int kLdaWarps = 4;
+constexpr int kMaxClasses = 9;
+
+struct LdaGeom {
+    int n_bins, n_classes, n_features, n_levels;
+    int n_windows, n_channels, n_rows, first_row, order, step;
+    int smooth_radius;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kLdaFrames * kLdaWarps)
+k_lda_decode(const double* __restrict__ feat, const double* __restrict__ Wt /*[bin][F][KC]*/,
+             const double* __restrict__ bias /*[bin][KC]*/, const double* __restrict__ cls /*[bin][KC]*/,
+             const int* __restrict__ select, const double* __restrict__ medians, const double* __restrict__ taps,
+             double* __restrict__ labels, double* __restrict__ spec, int smooth, const LdaGeom g) {
+    extern __shared__ double sm[];
+    double* xs = sm;                                   // [F][33]
+    double* raw = sm + (size_t)g.n_features * 33;      // [n_bins][33]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sess = blockIdx.y;
+    const int row0 = blockIdx.x * kLdaFrames;
+    const int row = row0 + lane;
+    const bool live = row < g.n_rows;
+    const double* fs = feat + (long long)sess * g.n_windows * g.n_channels;
+
+    // gather the selected, stacked features of 32 frames
+    for (int f = warp; f < g.n_features; f += kLdaWarps) {
+        const int col = select[f];
+        const int c = col / (g.order + 1), tap = col - c * (g.order + 1);
+        const int w = row + g.first_row - (g.order - tap) * g.step;
+        xs[f * 33 + lane] = (live && w >= 0) ? fs[(long long)w * g.n_channels + c] : 0.0;
+    }
+    __syncthreads();
+
+    for (int b = warp; b < g.n_bins; b += kLdaWarps) {
+        double acc[KC];
+        const double* bb = bias + b * KC;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[k] = 0.0;
+        const double* wb = Wt + (long long)b * g.n_features * KC;
+        for (int f = 0; f < g.n_features; ++f) {
+            const double xv = xs[f * 33 + lane];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) acc[k] = fma(xv, __ldg(wb + f * KC + k), acc[k]);
+        }
+        int best = 0;
+        double bv = acc[0] + bb[0];
+#pragma unroll
+        for (int k = 1; k < KC; ++k) {
+            const double s = acc[k] + bb[k];
+            if (s > bv) { bv = s; best = k; }              // strict: the first maximum wins, as numpy argmax
+        }
+        const double lab = cls[b * KC + best];
+        if (live && labels) labels[((long long)sess * g.n_rows + row) * g.n_bins + b] = lab;
+        int lv = (int)lab;
+        lv = lv < 0 ? 0 : (lv >= g.n_levels ? g.n_levels - 1 : lv);
+        raw[b * 33 + lane] = medians[b * g.n_levels + lv];
+    }
+    if (!spec) return;
+    __syncthreads();
+    for (int b = warp; b < g.n_bins; b += kLdaWarps) {
+        double v = raw[b * 33 + lane];
+        if (smooth) {
+            // scipy.ndimage correlate1d, symmetric-kernel branch: centre tap first, then pairs from the far end in;
+            // separate multiply and add (no FMA) so the result is bit-identical to the C loop
+            const int R = g.smooth_radius;
+            auto at = [&](int i) {                          // 'reflect': d c b a | a b c d | d c b a
+                if (i < 0) i = -i - 1;
+                if (i >= g.n_bins) i = 2 * g.n_bins - 1 - i;
+                return raw[i * 33 + lane];
+            };
+            double t = __dmul_rn(v, taps[R]);
+            for (int jj = -R; jj < 0; ++jj) t = __dadd_rn(t, __dmul_rn(__dadd_rn(at(b + jj), at(b - jj)), taps[R + jj]));
+            v = t;
+        }
+        if (live) spec[((long long)sess * g.n_rows + row) * g.n_bins + b] = v;
+    }
+}
+
+int lda_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select,
+            const double* medians, const double* taps, double* labels, double* spec, int smooth, int n_sessions,
+            const LdaGeom& g, cudaStream_t st) {
+    if (g.n_rows <= 0) return SGS_OK;
+    const size_t smem = sizeof(double) * 33 * ((size_t)g.n_features + g.n_bins);
+    if (smem > 200 * 1024) { set_error("too many features (%d) for the LDA kernel", g.n_features); return SGS_ERR_UNSUPPORTED; }
+    if (g.n_classes != kMaxClasses) { set_error("LDA kernel is built for %d classes per bin (got %d)", kMaxClasses, g.n_classes); return SGS_ERR_UNSUPPORTED; }
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_lda_decode<kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    dim3 grid(ceil_div(g.n_rows, kLdaFrames), n_sessions);
+    k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g);
+    SGS_LAUNCHED();
+    SGS_CUDA(cudaGetLastError());
+    return SGS_OK;
+}
+
+}  // namespace sgs

@@ -60,6 +60,16 @@ def sosfilt_host(sos, x, zi):
     return y, zi
 
 
+def propagate(M, n):
+    """M^n by n sequential multiplications.  Repeated squaring (numpy.linalg.matrix_power) is numerically
+    useless here: these transition matrices are highly non-normal (transient growth 1e3..1e6 before the decay),
+    and squaring amplifies the rounding error by |M^(n/2)|^2."""
+    X = np.eye(M.shape[0])
+    for _ in range(int(n)):
+        X = M @ X
+    return X
+
+
 class FeaturePlan:
     """All constants of one feature-extraction configuration (sample rate, window, shift, line noise)."""
 

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 from . import _lib
-from .design import FeaturePlan
+from .design import FeaturePlan, propagate
 
 SM_COUNT = 148
 STREAMS_PER_BLOCK = 32          # csrc/feat.cu: one CTA = 4 stage-warps x 32 streams
@@ -78,7 +78,7 @@ class FeatureExtractor:
     def horizon(self):
         """Smallest multiple of 1024 samples after which the influence of a state is below carry_tol."""
         if self._horizon is None:
-            P = np.linalg.matrix_power(self.transition(), 1024)
+            P = propagate(self.transition(), 1024)
             M, w = P.copy(), 1024
             while np.abs(M).max() > self.carry_tol and w < (1 << 22):
                 M = M @ P
@@ -88,7 +88,7 @@ class FeatureExtractor:
 
     def phi(self, chunk_len):
         if chunk_len not in self._phi:
-            self._phi[chunk_len] = np.ascontiguousarray(np.linalg.matrix_power(self.transition(), int(chunk_len)))
+            self._phi[chunk_len] = np.ascontiguousarray(propagate(self.transition(), int(chunk_len)))
         return self._phi[chunk_len]
 
     def scan_plan(self, n_samples, n_streams, chunks=None, horizon=None):

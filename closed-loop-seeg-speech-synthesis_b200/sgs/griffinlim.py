@@ -1,0 +1,107 @@
+"""Griffin-Lim operators on top of libsgs: node semantics (sgs_gl_node_synthesize) and the batch form."""
+import numpy as np
+
+from . import _lib
+from .design import GriffinLimNodePlan, propagate
+
+LP_CHUNK = 2048
+
+
+def lowpass_transition(b, a):
+    """Zero-input state transition of scipy.signal.lfilter's direct-form-II-transposed recurrence."""
+    order = len(a) - 1
+    M = np.zeros((order, order))
+    for i in range(order):
+        M[i, 0] = -a[i + 1]
+        if i + 1 < order:
+            M[i, i + 1] = 1.0
+    return M
+
+
+class GriffinLimNodeOp:
+    """Batched equivalent of GriffinLimSynthesis fed frame by frame (livenodes/GriffinLim.py)."""
+
+    def __init__(self, frame_size_ms=16, frame_shift_ms=10, sample_rate=16000, n_mels=40, iterations=5, cutoff=7900,
+                 norm_factor=1.0):
+        self.plan = GriffinLimNodePlan(frame_size_ms, frame_shift_ms, sample_rate, n_mels, iterations, 0, cutoff, norm_factor)
+        p = self.plan
+        self.first_frame = p.block_len - p.context_width - 1
+        self.order = len(p.lp_a) - 1
+        self.n_mels = n_mels
+        self._handle = None
+
+    def handle(self):
+        if self._handle is None:
+            _lib.ensure_init()
+            p = self.plan
+            a0 = p.lp_a[0]
+            b = np.ascontiguousarray(p.lp_b / a0, dtype=np.float64)
+            a = np.ascontiguousarray(p.lp_a / a0, dtype=np.float64)
+            phi = np.ascontiguousarray(propagate(lowpass_transition(b, a), LP_CHUNK))
+            win = np.ascontiguousarray(p.window, dtype=np.float64)
+            ola = np.ascontiguousarray(p.ola_window, dtype=np.float64)
+            idx = np.ascontiguousarray(p.mel.inv_idx, dtype=np.int32)
+            w = np.ascontiguousarray(p.mel.inv_w, dtype=np.float64)
+            h = _lib.c_void_p()
+            _lib.check(_lib.lib().sgs_gl_node_create(
+                _lib.C.byref(h), p.fft_size, p.hop, p.block_len, p.context_width, self.n_mels, _lib.ptr(win), _lib.ptr(ola),
+                _lib.ptr(idx), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a), self.order, _lib.ptr(phi), LP_CHUNK,
+                float(p.norm_factor * 1.01), p.iterations))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.lib().sgs_gl_node_destroy(self._handle)
+        except Exception:
+            pass
+
+    def positions(self, n_frames, start_ms=0.0):
+        """Write-head position after each frame, with the node's float expression (GriffinLim.py:115-120)."""
+        p = self.plan
+        pos = np.empty(n_frames, dtype=np.int32)
+        ms = start_ms
+        for k in range(n_frames):
+            ms += p.frame_shift_ms
+            pos[k] = int((ms / 1000.0) * p.sample_rate)
+        return pos
+
+    def synthesize(self, logmel, noise=None, seed=0, want_filtered=False, want_blocks=False):
+        """logmel (.., T, n_mels) float64 (numpy or torch-CUDA); noise (.., T, 480) or None.
+        Returns int16 PCM (.., n_out) [, filtered float64] [, blocks (.., T, 480)]."""
+        is_torch = _lib._is_torch(logmel)
+        squeeze = logmel.ndim == 2
+        if squeeze:
+            logmel = logmel[None]
+            noise = None if noise is None else noise[None]
+        S, T, nm = logmel.shape
+        assert nm == self.n_mels
+        pos = self.positions(T)
+        n_out = int(pos[-1] - pos[self.first_frame - 1]) if T > self.first_frame else 0
+        if is_torch:
+            import torch
+            logmel = logmel.contiguous()
+            assert logmel.dtype == torch.float64
+            pcm = torch.empty((S, n_out), dtype=torch.int16, device=logmel.device)
+            flt = torch.empty((S, n_out), dtype=torch.float64, device=logmel.device) if want_filtered else None
+            blk = torch.empty((S, T, 480), dtype=torch.float64, device=logmel.device) if want_blocks else None
+            if noise is not None:
+                noise = noise.contiguous()
+        else:
+            logmel = np.ascontiguousarray(logmel, dtype=np.float64)
+            pcm = np.empty((S, n_out), dtype=np.int16)
+            flt = np.empty((S, n_out), dtype=np.float64) if want_filtered else None
+            blk = np.empty((S, T, 480), dtype=np.float64) if want_blocks else None
+            if noise is not None:
+                noise = np.ascontiguousarray(noise, dtype=np.float64)
+        if n_out > 0:
+            _lib.check(_lib.lib().sgs_gl_node_synthesize(self.handle(), _lib.ptr(logmel), S, T, _lib.ptr(pos), _lib.ptr(noise),
+                                                         int(seed), None, _lib.ptr(pcm), _lib.ptr(flt), _lib.ptr(blk),
+                                                         _lib.current_stream(logmel)))
+        out = [pcm[0] if squeeze else pcm]
+        if want_filtered:
+            out.append(flt[0] if squeeze else flt)
+        if want_blocks:
+            out.append(blk[0] if squeeze else blk)
+        return out[0] if len(out) == 1 else tuple(out)

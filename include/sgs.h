@@ -70,6 +70,60 @@ int sgs_feat_extract(sgs_feat_plan* plan, const void* x, int x_is_f64, int64_t n
 int sgs_feat_stack(const double* feat, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,
                    int order, int step, double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Per-mel-bin LDA decoding + dequantisation (+ optional smoothing across bins).
+ * Replaces: 40 x sklearn LinearDiscriminantAnalysis.predict per frame (livenodes/LDASynthesis.py:25-26),
+ *           medians lookup + scipy.ndimage.gaussian_filter (livenodes/Dequantization.py:16-17),
+ *           local/quantization.py:125-135 (dequantize_spectrogram, no smoothing).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct sgs_lda_model sgs_lda_model;
+
+/* W[n_bins][n_classes][n_features], bias[n_bins][n_classes] (-inf for classes a bin never saw),
+ * class_labels[n_bins][n_classes] (the label value each score row stands for), select[n_features] = column of the
+ * stacked feature vector (c*(order+1)+tap) each model feature reads, medians[n_bins][n_levels],
+ * smooth_taps[2*smooth_radius+1] (NULL / 0 = model cannot smooth).  Binary estimators are packed by the caller
+ * as the two rows {0, coef_} / {0, intercept_}. */
+int sgs_lda_model_create(sgs_lda_model** model, int n_bins, int n_classes, int n_features, const double* W,
+                         const double* bias, const double* class_labels, const int32_t* select, const double* medians,
+                         int n_levels, const double* smooth_taps, int smooth_radius);
+void sgs_lda_model_destroy(sgs_lda_model* model);
+
+/* feat: un-stacked log-power [n_sessions][n_windows][n_channels] (output of sgs_feat_extract); row r of the
+ * stacked view is assembled on the fly exactly as sgs_feat_stack would (first_row/order/step as there; pass
+ * order = 0, first_row = 0 to decode already-stacked rows of width n_channels).
+ * labels, spec: [n_sessions][n_rows][n_bins] fp64, either may be NULL.  smooth != 0 applies the taps across bins
+ * with scipy's 'reflect' boundary. */
+int sgs_lda_decode(const sgs_lda_model* model, const double* feat, int n_sessions, int n_windows, int n_channels,
+                   int n_rows, int first_row, int order, int step, double* labels, double* spec, int smooth,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Griffin-Lim, streaming-node semantics (livenodes/GriffinLim.py:13-174), batched over frames and sessions.
+ * Replaces: numpy.fft.rfft/irfft + np.angle/np.exp per frame (GriffinLim.py:64-96), the ring-buffer overlap-add
+ *           (GriffinLim.py:145-166), scipy.signal.lfilter + int16 conversion (GriffinLim.py:169-174).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct sgs_gl_node sgs_gl_node;
+
+/* window = blackman(fft_size); ola_window = blackman(block_len*hop); inv_idx/inv_w[bins][2] = the (at most two)
+ * non-zero entries of MelFilterBank.melInvMatrix per spectral bin; lp_b/lp_a[lp_order+1] = the output low-pass;
+ * lp_phi[lp_order^2] = (zero-input DF2T state transition)^lp_chunk for the chunked scan; norm_div = normFactor*1.01.
+ * Only the configuration decode.py uses is built: fft 256, hop 160, block_len 3, context_width 1. */
+int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len, int context_width, int n_mels,
+                       const double* window, const double* ola_window, const int32_t* inv_idx, const double* inv_w,
+                       const double* lp_b, const double* lp_a, int lp_order, const double* lp_phi, int lp_chunk,
+                       double norm_div, int iterations);
+void sgs_gl_node_destroy(sgs_gl_node* node);
+
+/* logmel[n_sessions][n_frames][n_mels]; positions[n_frames] = write-head position after each frame (host table:
+ * int((ms/1000)*sampleRate) with ms accumulated as the node does); noise[n_sessions][n_frames][480] = the
+ * np.random.rand(480) draw of each frame (row 0 unused) or NULL to draw from the counter-based generator with
+ * `seed`.  lp_state[n_sessions][lp_order] (host, in/out, NULL = start from rest).  Outputs per session:
+ * n_out = positions[n_frames-1] - positions[0] samples: pcm int16, optionally the un-quantised low-passed signal
+ * (`filtered`) and the raw 480-sample blocks (`blocks_out`, [n_sessions][n_frames][480]). */
+int sgs_gl_node_synthesize(sgs_gl_node* node, const double* logmel, int n_sessions, int n_frames,
+                           const int32_t* positions, const double* noise, uint64_t seed, double* lp_state,
+                           int16_t* pcm, double* filtered, double* blocks_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,123 @@
+"""CUDA LDA decoding, dequantisation and node-semantics Griffin-Lim against the oracle and reference fixtures."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle as O
+from sgs import synth
+from sgs.features import FeatureExtractor
+from sgs.lda import LdaDecoder, pack_estimators
+from sgs.griffinlim import GriffinLimNodeOp
+from helpers import load, node_noise, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def model():
+    G = load('train_decode.npz')
+    with open(os.path.join(GOLDEN, 'estimators.pkl'), 'rb') as fh:
+        est = pickle.load(fh)
+    return G, est
+
+
+def test_lda_labels_and_spectrum_match_reference_fixture(model):
+    """Class indices are bit-exact against the reference's sklearn predict on its own streamed features."""
+    G, est = model
+    dec = LdaDecoder(est, G['select'], G['medians'])
+    labels, spec = dec.decode(G['dec_feat'], smooth=True)          # already stacked rows (300 x 150)
+    assert np.array_equal(labels, G['dec_labels'])
+    assert np.array_equal(spec, G['dec_spec'])                      # lookup + scipy-ordered 5-tap smoothing: bit-exact
+    labels_b, spec_b = dec.decode(G['dec_feat'], smooth=False)
+    assert np.array_equal(spec_b, O.dequantize_spectrogram(labels_b, G['medians']))
+
+
+def test_lda_fused_gather_from_unstacked_features(model):
+    """Decoding straight from the un-stacked log-power array equals stack -> select -> predict (offline and online views)."""
+    G, est = model
+    sr, bad = int(G['sr']), list(G['bad'])
+    x = np.delete(synth.seeg_session(2, int(G['n_ch']), sr, 3.0), bad, axis=1)
+    fe = FeatureExtractor(sr)
+    dec = LdaDecoder(est, G['select'], G['medians'])
+    lp = fe.log_power(x)
+    lab_off, spec_off = dec.decode(lp, order=4, step=5, first_row=20)
+    assert np.array_equal(lab_off, G['batch_labels'])
+    assert np.array_equal(spec_off, G['batch_spec'])
+    lp_on = fe.log_power(x, online=True, chunk_size=32)
+    lab_on, spec_on = dec.decode(lp_on, order=4, step=5, first_row=0, smooth=True)
+    assert np.array_equal(lab_on, G['dec_labels'])
+    assert np.array_equal(spec_on, G['dec_spec'])
+
+
+def test_lda_missing_and_binary_classes():
+    """Bins that never saw some classes (train.py:86-91) and sklearn's two-class special case."""
+    from sklearn.discriminant_analysis import LinearDiscriminantAnalysis
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(600, 12))
+    ys = [rng.integers(0, 9, 600), rng.choice([0, 3, 4, 8], 600), rng.choice([2, 7], 600)]
+    for y in ys:
+        X[np.arange(600), y % 12] += 1.5
+    est = [LinearDiscriminantAnalysis().fit(X, y.astype(float)) for y in ys]
+    med = np.tile(np.linspace(-12, -3, 9), (3, 1))
+    dec = LdaDecoder(est, np.arange(12), med)
+    Xt = rng.normal(size=(257, 12))
+    labels, spec = dec.decode(Xt)
+    want = O.lda_predict(Xt, est, np.arange(12))
+    assert np.array_equal(labels, want)
+    assert np.array_equal(spec, O.dequantize_spectrogram(want, med))
+    W, b, cls = pack_estimators(est)
+    assert np.isinf(b[1]).sum() == 5 and np.isinf(b[2]).sum() == 7
+
+
+def test_griffinlim_node_against_reference_fixture():
+    GL = load('griffinlim.npz')
+    lm = GL['node_logmel']
+    for norm in (1.0, 10.0):
+        op = GriffinLimNodeOp(16, 10, 16000, 40, iterations=8, norm_factor=norm)
+        pcm = op.synthesize(lm, node_noise(77, len(lm)))
+        want = GL['node_pcm_norm%g' % norm]
+        assert pcm.shape == want.shape
+        d = np.abs(pcm.astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3          # int16 truncation may flip one LSB on a rounding boundary
+    op = GriffinLimNodeOp(16, 10, 16000, 40)                   # default 5 iterations
+    lm2 = GL['node5_logmel']
+    d = np.abs(op.synthesize(lm2, node_noise(78, len(lm2))).astype(int) - GL['node5_pcm'].astype(int))
+    assert d.max() <= 1
+
+
+def test_griffinlim_node_long_stream_against_oracle(model):
+    """300 frames (crosses the 159/161-sample hops of quirk Q7 at frame 201) + float comparison of blocks."""
+    G, _ = model
+    spec = G['dec_spec']
+    noise = node_noise(4001, len(spec))
+    op = GriffinLimNodeOp(16, 10, 16000, 40, iterations=8, norm_factor=10)
+    pcm, flt, blk = op.synthesize(spec, noise, want_filtered=True, want_blocks=True)
+    ref = O.GriffinLimNode(16, 10, 16000, 40, 8, norm_factor=10)
+    want_pcm, want_flt = ref.synthesize(spec, noise)
+    assert pcm.shape == G['dec_audio'].shape
+    want_blk = ref.block(spec[9:11], noise[10])
+    assert np.abs(blk[10] - want_blk).max() <= 1e-11 * np.abs(want_blk).max()
+    # the reference's 'ba'-form low-pass has clustered poles near z = -1 (state gain ~6e5): fp64 round-off differences
+    # (FMA vs separate multiply-add) are amplified to ~1e-10 relative
+    assert np.abs(flt - want_flt).max() <= 1e-8 * np.abs(want_flt).max()
+    d = np.abs(pcm.astype(int) - G['dec_audio'].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+def test_griffinlim_sessions_batch_and_device_noise():
+    import torch
+    med = synth.default_medians()
+    lm = synth.logmel_utterances(3, 25, med, seed=3200)
+    noise = np.stack([node_noise(90 + s, 25) for s in range(3)])
+    op = GriffinLimNodeOp(16, 10, 16000, 40, iterations=8, norm_factor=10)
+    pcm = op.synthesize(lm, noise)
+    for s in range(3):
+        want, _ = O.GriffinLimNode(16, 10, 16000, 40, 8, norm_factor=10).synthesize(lm[s], noise[s])
+        assert np.abs(pcm[s].astype(int) - want.astype(int)).max() <= 1
+    # device-resident input + counter-based noise: runs, deterministic per seed, differs across seeds
+    a = op.synthesize(torch.from_numpy(lm).cuda(), None, seed=1)
+    b = op.synthesize(torch.from_numpy(lm).cuda(), None, seed=1)
+    c = op.synthesize(torch.from_numpy(lm).cuda(), None, seed=2)
+    assert a.is_cuda and torch.equal(a, b) and not torch.equal(a, c)
