@@ -201,3 +201,87 @@ int sgs_feat_stack(const double* feat, int n_sessions, int n_windows, int n_chan
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// streaming feature extraction (ECogFeatCalc node)
+// ---------------------------------------------------------------------------------------------------------------
+namespace sgs {
+constexpr int kSqRing = 256, kFeatRing = 32, kMaxFramesPerPush = 16;
+struct StreamFrames { int n; long long end[kMaxFramesPerPush]; long long index[kMaxFramesPerPush]; };
+int feat_stream_run(int n_biquads, const void* x, bool x_is_f64, int n, int n_channels, long long t0, double* z,
+                    double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int frame_size, int order, int step,
+                    double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st);
+}  // namespace sgs
+
+struct sgs_feat_stream {
+    sgs_feat_plan* plan = nullptr;
+    int n_channels = 0, frame_size = 0, order = 0, step = 0;
+    long long consumed = 0;
+    double *d_z = nullptr, *d_sq = nullptr, *d_feat = nullptr, *d_out = nullptr;
+    void* d_x = nullptr;
+    size_t x_cap = 0;
+};
+
+extern "C" {
+
+void sgs_feat_stream_destroy(sgs_feat_stream* s) {
+    if (!s) return;
+    cudaFree(s->d_z); cudaFree(s->d_sq); cudaFree(s->d_feat); cudaFree(s->d_out); cudaFree(s->d_x);
+    delete s;
+}
+
+int sgs_feat_stream_create(sgs_feat_stream** stream_out, sgs_feat_plan* plan, int n_channels, int frame_size, int order, int step) {
+    using namespace sgs;
+    SGS_ARG(stream_out && plan && n_channels >= 1, "bad arguments");
+    SGS_ARG(frame_size >= 1 && frame_size + 128 <= kSqRing, "frame_size %d too long for the streaming ring", frame_size);
+    SGS_ARG(order >= 0 && step >= 1 && order * step + 1 <= kFeatRing, "context %d x %d too long", order, step);
+    sgs_feat_stream* s = new sgs_feat_stream();
+    s->plan = plan; s->n_channels = n_channels; s->frame_size = frame_size; s->order = order; s->step = step;
+    const size_t C = n_channels;
+    cudaError_t e = cudaMalloc((void**)&s->d_z, sizeof(double) * 2 * plan->n_biquads * C);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_sq, sizeof(double) * kSqRing * C);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_feat, sizeof(double) * kFeatRing * C);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_out, sizeof(double) * kMaxFramesPerPush * C * (order + 1));
+    if (e == cudaSuccess) e = cudaMemset(s->d_feat, 0, sizeof(double) * kFeatRing * C);
+    if (e != cudaSuccess) { sgs_feat_stream_destroy(s); return cuda_fail(e, "stream state", __FILE__, __LINE__); }
+    *stream_out = s;
+    return SGS_OK;
+}
+
+/* x: n x n_channels new samples (host).  frame_ends[n_frames] = exclusive end positions, in real-sample coordinates,
+ * of the frames this push completes (host schedule, FrameBuffer.py:177); frame_index[n_frames] their running numbers.
+ * out: n_frames x (n_channels*(order+1)) stacked rows (host). */
+int sgs_feat_stream_push(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
+                         const int64_t* frame_index, int n_frames, double* out, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(s && x && n >= 1, "bad arguments");
+    SGS_ARG(n_frames >= 0 && n_frames <= kMaxFramesPerPush && (n_frames == 0 || (frame_ends && frame_index && out)), "bad frame schedule");
+    SGS_ARG(n <= 128, "push at most 128 samples per call (got %d)", n);
+    const size_t esz = x_is_f64 ? 8 : 4, bytes = (size_t)n * s->n_channels * esz;
+    if (s->x_cap < bytes) {
+        if (s->d_x) SGS_CUDA(cudaFree(s->d_x));
+        SGS_CUDA(cudaMalloc(&s->d_x, bytes * 2));
+        s->x_cap = bytes * 2;
+    }
+    StreamFrames fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.n = n_frames;
+    for (int q = 0; q < n_frames; ++q) {
+        SGS_ARG(frame_ends[q] <= s->consumed + n && frame_ends[q] > s->consumed - 128, "frame %d does not end inside this push", q);
+        fr.end[q] = frame_ends[q];
+        fr.index[q] = frame_index[q];
+    }
+    SGS_CUDA(cudaMemcpyAsync(s->d_x, x, bytes, cudaMemcpyHostToDevice, st));
+    int rc = feat_stream_run(s->plan->n_biquads, s->d_x, x_is_f64 != 0, n, s->n_channels, s->consumed, s->d_z, s->d_sq, s->d_feat,
+                             s->plan->d_zf, s->plan->zero_fill, s->frame_size, s->order, s->step, s->d_out, s->plan->cf, fr, st);
+    if (rc != SGS_OK) return rc;
+    s->consumed += n;
+    if (n_frames > 0) {
+        SGS_CUDA(cudaMemcpyAsync(out, s->d_out, sizeof(double) * (size_t)n_frames * s->n_channels * (s->order + 1), cudaMemcpyDeviceToHost, st));
+        SGS_CUDA(cudaStreamSynchronize(st));
+    }
+    return SGS_OK;
+}
+
+}  // extern "C"

@@ -1,5 +1,6 @@
 // C ABI for Griffin-Lim synthesis (include/sgs.h).
 #include <math.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 #include "fft.cuh"
@@ -11,7 +12,14 @@ constexpr int kLpMaxOrd = 8;
 struct GlNodeTables { const double* window; const cplx* tw_half; const cplx* tw_full; const int* inv_idx; const double* inv_w; };
 struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
 int gl_blocks_run(const double* logmel, const double* noise, unsigned long long seed, double* blocks, const GlNodeTables& tab,
-                  int n_sessions, int n_frames, int n_mels, int first_frame, int iters, cudaStream_t st);
+                  int n_sessions, int n_frames, int n_mels, int first_frame, int iters, long long ring_base, int ring_len,
+                  cudaStream_t st);
+constexpr int kMaxFramesPerPush = 16, kBlockRing = 8;
+struct EmitFrames { int n; long long index[kMaxFramesPerPush]; int pos[kMaxFramesPerPush]; int prev[kMaxFramesPerPush]; int ring_pos[kBlockRing]; long long ring_index[kBlockRing]; };
+int gl_emit_stream_run(const double* block_ring, const double* ola_window, double* lp_state, short* pcm, const LpCoefs& c,
+                       double norm_div, int first_frame, const EmitFrames& fr, cudaStream_t st);
+int dequantize_run(const double* labels, const double* medians, const double* taps, int radius, int smooth, int n_bins,
+                   int n_levels, long long n_rows, double* out, cudaStream_t st);
 int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, double* v, double* states, double* zi,
                 const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered, int n_sessions, int n_frames,
                 int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st);
@@ -25,6 +33,12 @@ struct sgs_gl_node {
     sgs::cplx *d_tw_half = nullptr, *d_tw_full = nullptr;
     int* d_inv_idx = nullptr;
     int lp_chunk = 0;
+    // streaming state (sgs_gl_node_push): previous spectral frame + new ones, block ring, low-pass state
+    double *d_mel = nullptr, *d_ring = nullptr, *d_lp = nullptr, *d_noise = nullptr;
+    short* d_pcm = nullptr;
+    long long frames_seen = 0;
+    int ring_pos[sgs::kBlockRing];
+    long long ring_index[sgs::kBlockRing];
 };
 
 static cudaError_t upload(void** dst, const void* src, size_t bytes) {
@@ -39,6 +53,7 @@ void sgs_gl_node_destroy(sgs_gl_node* n) {
     if (!n) return;
     cudaFree(n->d_window); cudaFree(n->d_ola); cudaFree(n->d_inv_w); cudaFree(n->d_phi);
     cudaFree(n->d_tw_half); cudaFree(n->d_tw_full); cudaFree(n->d_inv_idx);
+    cudaFree(n->d_mel); cudaFree(n->d_ring); cudaFree(n->d_lp); cudaFree(n->d_noise); cudaFree(n->d_pcm);
     delete n;
 }
 
@@ -77,6 +92,14 @@ int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len,
     if (e == cudaSuccess) e = upload((void**)&n->d_tw_half, th.data(), sizeof(cplx) * kHalf);
     if (e == cudaSuccess) e = upload((void**)&n->d_tw_full, tf.data(), sizeof(cplx) * kBins);
     if (e == cudaSuccess) e = upload((void**)&n->d_phi, lp_phi, sizeof(double) * lp_order * lp_order);
+    for (int i = 0; i < kBlockRing; ++i) { n->ring_pos[i] = 0; n->ring_index[i] = -1; }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&n->d_mel, sizeof(double) * (kMaxFramesPerPush + 1) * n_mels);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&n->d_ring, sizeof(double) * kBlockRing * kBlk);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&n->d_noise, sizeof(double) * (kMaxFramesPerPush + 1) * kBlk);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&n->d_pcm, sizeof(short) * kMaxFramesPerPush * 192);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&n->d_lp, sizeof(double) * kLpMaxOrd);
+    if (e == cudaSuccess) e = cudaMemset(n->d_lp, 0, sizeof(double) * kLpMaxOrd);
+    if (e == cudaSuccess) e = cudaMemset(n->d_mel, 0, sizeof(double) * (kMaxFramesPerPush + 1) * n_mels);
     if (e != cudaSuccess) { sgs_gl_node_destroy(n); return cuda_fail(e, "table upload", __FILE__, __LINE__); }
     *node = n;
     return SGS_OK;
@@ -124,7 +147,7 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
     if (rc == SGS_OK) {
         GlNodeTables tab{n->d_window, n->d_tw_half, n->d_tw_full, n->d_inv_idx, n->d_inv_w};
         rc = gl_blocks_run((const double*)s_mel.dev, (const double*)s_noise.dev, seed, d_blocks, tab, n_sessions, n_frames,
-                           n->n_mels, first, n->iterations, st);
+                           n->n_mels, first, n->iterations, 0, 0, st);
     }
     if (rc == SGS_OK)
         rc = gl_emit_run(d_blocks, d_pos, n->d_ola, d_v, d_states, d_zi, n->d_phi, n->lp, n->norm_div, (short*)s_pcm.dev,
@@ -145,6 +168,77 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
     if (d_states) cudaFreeAsync(d_states, st);
     if (d_zi) cudaFreeAsync(d_zi, st);
     release(s_mel, st); release(s_noise, st); release(s_pcm, st); release(s_flt, st); release(s_blk, st);
+    if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+/* Streaming form: feed `n` new spectral frames (host), get the audio the node would have emitted for them. */
+int sgs_gl_node_push(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
+                     uint64_t seed, int16_t* pcm, int* n_pcm, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(s && logmel && pos && pcm && n_pcm, "NULL argument");
+    SGS_ARG(n >= 1 && n <= kMaxFramesPerPush, "push takes 1..%d frames (got %d)", kMaxFramesPerPush, n);
+    const int nm = s->n_mels, first = s->first_frame;
+    const long long k0 = s->frames_seen;
+    // row 0 of d_mel holds the previous frame; append the new ones behind it
+    SGS_CUDA(cudaMemcpyAsync(s->d_mel + nm, logmel, sizeof(double) * n * nm, cudaMemcpyHostToDevice, st));
+    if (noise) SGS_CUDA(cudaMemcpyAsync(s->d_noise + kBlk, noise, sizeof(double) * n * kBlk, cudaMemcpyHostToDevice, st));
+    EmitFrames fr;
+    memset(&fr, 0, sizeof(fr));
+    int total = 0, prev = pos_before;
+    // frames k0 .. k0+n-1; a block exists for k >= first (the node returns early before that, GriffinLim.py:131)
+    const int skip = (k0 < first) ? (int)std::min<long long>(first - k0, n) : 0;
+    for (int i = 0; i < n; ++i) {
+        SGS_ARG(pos[i] > prev && pos[i] - prev <= 192, "bad write-head position at new frame %d", i);
+        if (i >= skip) {
+            const long long k = k0 + i;
+            const int q = fr.n++;
+            fr.index[q] = k; fr.pos[q] = pos[i]; fr.prev[q] = prev;
+            total += pos[i] - prev;
+            s->ring_pos[k & (kBlockRing - 1)] = pos[i];
+            s->ring_index[k & (kBlockRing - 1)] = k;
+        }
+        prev = pos[i];
+    }
+    for (int i = 0; i < kBlockRing; ++i) { fr.ring_pos[i] = s->ring_pos[i]; fr.ring_index[i] = s->ring_index[i]; }
+    int rc = SGS_OK;
+    if (fr.n > 0) {
+        GlNodeTables tab{s->d_window, s->d_tw_half, s->d_tw_full, s->d_inv_idx, s->d_inv_w};
+        // local frame j (row j of d_mel) is running frame k0 - 1 + j; blocks for local frames [1 + skip, n]
+        rc = gl_blocks_run(s->d_mel, noise ? s->d_noise : nullptr, seed, s->d_ring, tab, 1, n + 1, nm, 1 + skip, s->iterations,
+                           k0 - 1, kBlockRing, st);
+        if (rc == SGS_OK)
+            rc = gl_emit_stream_run(s->d_ring, s->d_ola, s->d_lp, s->d_pcm, s->lp, s->norm_div, first, fr, st);
+        if (rc == SGS_OK) SGS_CUDA(cudaMemcpyAsync(pcm, s->d_pcm, sizeof(short) * total, cudaMemcpyDeviceToHost, st));
+    }
+    // the newest frame becomes the "previous" one
+    SGS_CUDA(cudaMemcpyAsync(s->d_mel, s->d_mel + (size_t)n * nm, sizeof(double) * nm, cudaMemcpyDeviceToDevice, st));
+    s->frames_seen += n;
+    *n_pcm = total;
+    if (rc == SGS_OK) SGS_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int sgs_dequantize(const double* medians, int n_bins, int n_levels, const double* taps, int radius, const double* labels,
+                   int64_t n_rows, int smooth, double* out, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(medians && n_bins >= 1 && n_levels >= 1 && n_rows >= 0, "bad arguments");
+    SGS_ARG(!smooth || (taps && radius >= 1 && radius < n_bins), "smoothing taps missing");
+    if (n_rows == 0) return SGS_OK;
+    SGS_ARG(labels && out, "NULL argument");
+    Staged sm, stp, sl, so;
+    int rc = stage_in(sm, medians, sizeof(double) * n_bins * n_levels, st);
+    if (rc == SGS_OK && smooth) rc = stage_in(stp, taps, sizeof(double) * (2 * radius + 1), st);
+    if (rc == SGS_OK) rc = stage_in(sl, labels, sizeof(double) * (size_t)n_rows * n_bins, st);
+    if (rc == SGS_OK) rc = stage_out(so, out, sizeof(double) * (size_t)n_rows * n_bins, st);
+    if (rc == SGS_OK)
+        rc = dequantize_run((const double*)sl.dev, (const double*)sm.dev, (const double*)stp.dev, radius, smooth, n_bins, n_levels,
+                            n_rows, (double*)so.dev, st);
+    if (rc == SGS_OK) rc = finish_out(so, st);
+    const bool sync = so.host != nullptr;
+    release(sm, st); release(stp, st); release(sl, st); release(so, st);
     if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
     return rc;
 }

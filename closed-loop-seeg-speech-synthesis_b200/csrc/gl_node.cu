@@ -52,7 +52,7 @@ __device__ __forceinline__ double uniform01(unsigned long long seed, unsigned lo
 __global__ void __launch_bounds__(kGlWarps * 32)
 k_gl_blocks(const double* __restrict__ logmel, const double* __restrict__ noise, unsigned long long seed,
             double* __restrict__ blocks, const GlNodeTables tab, int n_frames, int n_mels, int first_frame, int iters,
-            long long n_items) {
+            long long n_items, long long ring_base, int ring_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_window = reinterpret_cast<double*>(smem_raw);                 // [256]
     cplx* s_tw_half = reinterpret_cast<cplx*>(s_window + kFft);             // [128]
@@ -91,7 +91,7 @@ k_gl_blocks(const double* __restrict__ logmel, const double* __restrict__ noise,
         }
         // start waveform
         for (int i = lane; i < kBlk; i += 32)
-            ws.x[i] = noise ? noise[frame * kBlk + i] : uniform01(seed, (unsigned long long)frame, (unsigned)i);
+            ws.x[i] = noise ? noise[frame * kBlk + i] : uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)i);
         __syncwarp();
 
         for (int it = 0; it < iters; ++it) {
@@ -165,7 +165,9 @@ k_gl_blocks(const double* __restrict__ logmel, const double* __restrict__ noise,
             for (int i = kHop + kFft + lane; i < kBlk; i += 32) ws.x[i] = 0.0;      // istft never reaches [416, 480)
             __syncwarp();
         }
-        for (int i = lane; i < kBlk; i += 32) blocks[frame * kBlk + i] = ws.x[i];
+        // batch: one row per (session, frame); streaming: slot of the running frame number in a power-of-two ring
+        const long long row = ring_len ? ((ring_base + k) & (ring_len - 1)) : frame;
+        for (int i = lane; i < kBlk; i += 32) blocks[row * kBlk + i] = ws.x[i];
         __syncwarp();
     }
 }
@@ -277,7 +279,8 @@ __global__ void k_lp_apply(const double* __restrict__ v, const double* __restric
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 int gl_blocks_run(const double* logmel, const double* noise, unsigned long long seed, double* blocks, const GlNodeTables& tab,
-                  int n_sessions, int n_frames, int n_mels, int first_frame, int iters, cudaStream_t st) {
+                  int n_sessions, int n_frames, int n_mels, int first_frame, int iters, long long ring_base, int ring_len,
+                  cudaStream_t st) {
     const long long n_items = (long long)n_sessions * (n_frames - first_frame);
     if (n_items <= 0) return SGS_OK;
     const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kHalf + kBins + 1) + sizeof(GlWarpSmem) * kGlWarps;
@@ -285,7 +288,7 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
     if (!attr) { cudaFuncSetAttribute(k_gl_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     long long want = (n_items + kGlWarps - 1) / kGlWarps;
     const int grid = (int)(want < 148 * 5 * 8 ? want : 148 * 5 * 8);
-    k_gl_blocks<<<grid, kGlWarps * 32, smem, st>>>(logmel, noise, seed, blocks, tab, n_frames, n_mels, first_frame, iters, n_items);
+    k_gl_blocks<<<grid, kGlWarps * 32, smem, st>>>(logmel, noise, seed, blocks, tab, n_frames, n_mels, first_frame, iters, n_items, ring_base, ring_len);
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;

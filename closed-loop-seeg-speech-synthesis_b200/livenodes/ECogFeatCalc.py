@@ -1,0 +1,117 @@
+"""Streaming high-gamma feature node with the reference's constructor and callback contract
+(livenodes/ECogFeatCalc.py:19-144).
+
+The reference wires three filtering FrameBuffers, a log-power LambdaNode, a 21-row stack FrameBuffer and a
+stacking LambdaNode behind this facade.  Here the whole sub-graph is one stateful device stream
+(sgs_feat_stream_push): filter states, the squared-signal history and the stack buffer stay in HBM between
+chunks; the host only keeps the fractional frame schedule of FrameBuffer.py:177.  Output per 10 ms frame:
+a 1-D float64 array of (model_order+1)*channels values in the reference's c*5+tap order."""
+import logging
+
+import numpy as np
+
+from . import Node
+from sgs import _lib
+from sgs.features import FeatureExtractor
+
+logger = logging.getLogger('ECoGFeatCalc.py')
+MAX_PUSH = 128      # samples per device push (csrc/stream.cu)
+
+
+class ECogFeatCalc(Node.Node):
+    def __init__(self, sample_rate, frame_len_ms, frame_shift_ms, model_order=4, step_size=5,
+                 line_noise=50, warm_start=True, chunk_size=32, has_inputs=True, name='ECogFeatCalc'):
+        super().__init__(name=name, has_inputs=has_inputs)
+        if not warm_start:
+            raise NotImplementedError("only the warm_start=True configuration used by decode.py is implemented")
+        self.sample_rate = sample_rate
+        self.frame_len_ms = frame_len_ms
+        self.frame_shift_ms = frame_shift_ms
+        self.model_order = model_order
+        self.step_size = step_size
+        self.chunk_size = int(chunk_size)
+        logger.info('Framelength in ms: ' + str(frame_len_ms))
+        logger.info('Frameshift in ms: ' + str(frame_shift_ms))
+        logger.info('Samplerate: ' + str(sample_rate))
+        self._fe = FeatureExtractor(sample_rate, line_noise=line_noise, model_order=model_order, step_size=step_size,
+                                    frame_len_ms=frame_len_ms, frame_shift_ms=frame_shift_ms)
+        plan = self._fe.plan
+        self.high_gamma_filter = plan.filters[0]
+        self.first_harmonic_filter = plan.filters[1]
+        self.second_harmonic_filter = plan.filters[2] if plan.n_filters == 3 else None
+        self._stream = None
+        self._pending = None            # samples not yet forming a complete chunk_size block (FrameBuffer semantics)
+        self._n_channels = None
+        self._consumed = 0              # samples handed to the device
+        self._frame_count = 0
+        sr = float(sample_rate)
+        self._first_ms = (float(plan.frame_size) / sr) * 1000.0             # FrameBuffer.py:35
+        self._next_end = plan.frame_size                                    # in zero-fill-prefixed coordinates
+
+    # -- device stream, created lazily in the process that pushes data (the graph may run in a forked child) --
+    def _open(self, n_channels):
+        h = _lib.c_void_p()
+        plan = self._fe.plan
+        _lib.check(_lib.lib().sgs_feat_stream_create(_lib.C.byref(h), self._fe.handle(), n_channels, plan.frame_size,
+                                                     self.model_order, self.step_size))
+        self._stream = h
+        self._n_channels = n_channels
+        self._out = np.empty((16, n_channels * (self.model_order + 1)), dtype=np.float64)
+
+    def reset_buffer(self):
+        """Forget all streaming state (the reference re-arms FrameBuffer.reset_buffer per input process)."""
+        if self._stream is not None:
+            _lib.lib().sgs_feat_stream_destroy(self._stream)
+        self._stream = None
+        self._pending = None
+        self._consumed = 0
+        self._frame_count = 0
+        self._next_end = self._fe.plan.frame_size
+
+    def __del__(self):
+        try:
+            if self._stream is not None:
+                _lib.lib().sgs_feat_stream_destroy(self._stream)
+        except Exception:
+            pass
+
+    def _schedule(self, n_new):
+        """Frames whose end falls inside the next n_new samples (FrameBuffer.py:147-177)."""
+        plan = self._fe.plan
+        total = plan.zero_fill + self._consumed + n_new
+        ends, idx = [], []
+        while self._next_end <= total and len(ends) < 16:
+            ends.append(self._next_end - plan.zero_fill)
+            idx.append(self._frame_count)
+            self._frame_count += 1
+            self._next_end = round(((self._first_ms + self._frame_count * float(self.frame_shift_ms)) / 1000.0)
+                                   * float(self.sample_rate))
+        return ends, idx
+
+    def add_data(self, data, data_id=None):
+        data = np.asarray(data)
+        if data.ndim == 1:
+            data = data.reshape(-1, 1)
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        if self._stream is None:
+            self._open(data.shape[1])
+        if self._pending is not None and len(self._pending):
+            data = np.vstack([self._pending, data])
+        usable = (len(data) // self.chunk_size) * self.chunk_size
+        self._pending = data[usable:].copy() if usable < len(data) else None
+        pos = 0
+        while pos < usable:
+            n = min(MAX_PUSH, usable - pos)
+            # keep at most 16 frames per push: shrink the push if a long chunk would complete more
+            ends, idx = self._schedule(n)
+            block = np.ascontiguousarray(data[pos:pos + n])
+            e = np.asarray(ends, dtype=np.int64)
+            k = np.asarray(idx, dtype=np.int64)
+            _lib.check(_lib.lib().sgs_feat_stream_push(self._stream, _lib.ptr(block), int(block.dtype == np.float64), n,
+                                                       _lib.ptr(e) if len(ends) else None, _lib.ptr(k) if len(ends) else None,
+                                                       len(ends), _lib.ptr(self._out), None))
+            self._consumed += n
+            pos += n
+            for q in range(len(ends)):
+                self.output_data(self._out[q].copy())

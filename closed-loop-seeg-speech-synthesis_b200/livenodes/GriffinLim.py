@@ -1,0 +1,60 @@
+"""Streaming Griffin-Lim synthesis node (reference: livenodes/GriffinLim.py:13-174).
+
+Each add_data pushes one log-mel frame to the device stream (sgs_gl_node_push), which synthesises that frame's
+480-sample block, overlap-adds it with the blocks still in its ring, applies the output low-pass with carried
+state and returns the int16 hop.  The initial waveform of every block is drawn with np.random.rand(480) on the
+host in the reference's order, so a seeded run reproduces the reference's audio; pass device_noise=True to draw
+on the device instead."""
+import time
+
+import numpy as np
+
+from . import Node
+from sgs import _lib
+from sgs.griffinlim import GriffinLimNodeOp
+
+
+class GriffinLimSynthesis(Node.Node):
+    def __init__(self, originalFrameSizeMs, frameShiftMs, sampleRate, melCoeffCount, numReconstructionIterations=5,
+                 extraContext=0, cutoff=7900, normFactor=1.0, useLogMels=True, name='GriffinLim', device_noise=False):
+        super().__init__(name=name)
+        if extraContext != 0 or not useLogMels:
+            raise NotImplementedError("only extraContext=0, useLogMels=True (decode.py:162-164) are implemented")
+        self._op = GriffinLimNodeOp(originalFrameSizeMs, frameShiftMs, sampleRate, melCoeffCount,
+                                    numReconstructionIterations, cutoff, normFactor)
+        plan = self._op.plan
+        self.useLogMels = useLogMels
+        self.frameShiftMs = float(frameShiftMs)
+        self.sampleRate = float(sampleRate)
+        self.fftSize = plan.fft_size
+        self.frameShift = plan.hop
+        self.contextWidth = plan.context_width
+        self.blockLen = plan.block_len
+        self.normFactor = normFactor
+        self.numReconstructionIterations = numReconstructionIterations
+        self.fftWindow = plan.window
+        self.filterNumerator, self.filterDenominator = plan.lp_b, plan.lp_a
+        self.outputBufferPosMs = 0
+        self.framePos = 0
+        self.rfc = 0
+        self.startTime = time.time()
+        self.device_noise = device_noise
+        self._pcm = np.empty(16 * 192, dtype=np.int16)
+
+    def add_data(self, dataFrame, data_id=0):
+        frame = np.ascontiguousarray(np.asarray(dataFrame, dtype=np.float64).reshape(1, -1))
+        self.framePos += 1
+        prev = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)
+        self.outputBufferPosMs += self.frameShiftMs
+        pos = np.array([int((self.outputBufferPosMs / 1000.0) * self.sampleRate)], dtype=np.int32)
+        first = self.framePos < self.blockLen - self.contextWidth
+        noise = None
+        if not first and not self.device_noise:
+            noise = np.random.rand(self.blockLen * self.frameShift)          # GriffinLim.py:90, same draw order
+        n_pcm = _lib.c_int(0)
+        _lib.check(_lib.lib().sgs_gl_node_push(self._op.handle(), _lib.ptr(frame), 1, _lib.ptr(pos), prev, _lib.ptr(noise),
+                                               self.framePos, _lib.ptr(self._pcm), _lib.C.byref(n_pcm), None))
+        if first:
+            return np.array([])
+        self.rfc += n_pcm.value
+        self.output_data(self._pcm[:n_pcm.value].copy())

@@ -70,6 +70,19 @@ int sgs_feat_extract(sgs_feat_plan* plan, const void* x, int x_is_f64, int64_t n
 int sgs_feat_stack(const double* feat, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,
                    int order, int step, double* out, void* stream);
 
+/* Streaming form (the ECogFeatCalc node: livenodes/ECogFeatCalc.py:67-104 over livenodes/FrameBuffer.py:60-177).
+ * All filter state, the y^2 history and the 21-row stack buffer stay on the device between pushes.
+ * x: n x n_channels new samples (host, n <= 128); frame_ends[n_frames]: exclusive end (in real-sample
+ * coordinates; the warm-start zero fill is negative) of every frame this push completes and frame_index[] their
+ * running numbers - the host keeps the reference's fractional frame schedule (FrameBuffer.py:177);
+ * out: n_frames x (n_channels*(order+1)) stacked rows (host).  Synchronous when n_frames > 0. */
+typedef struct sgs_feat_stream sgs_feat_stream;
+int sgs_feat_stream_create(sgs_feat_stream** stream_out, sgs_feat_plan* plan, int n_channels, int frame_size, int order,
+                           int step);
+void sgs_feat_stream_destroy(sgs_feat_stream* s);
+int sgs_feat_stream_push(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
+                         const int64_t* frame_index, int n_frames, double* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Per-mel-bin LDA decoding + dequantisation (+ optional smoothing across bins).
  * Replaces: 40 x sklearn LinearDiscriminantAnalysis.predict per frame (livenodes/LDASynthesis.py:25-26),
@@ -123,6 +136,19 @@ void sgs_gl_node_destroy(sgs_gl_node* node);
 int sgs_gl_node_synthesize(sgs_gl_node* node, const double* logmel, int n_sessions, int n_frames,
                            const int32_t* positions, const double* noise, uint64_t seed, double* lp_state,
                            int16_t* pcm, double* filtered, double* blocks_out, void* stream);
+
+/* Streaming form (GriffinLimSynthesis.add_data): feed n (1..16) new spectral frames, receive the audio the node
+ * emits for them.  pos[n] = write head after each new frame, pos_before = write head before the first of them;
+ * noise[n][480] or NULL (counter-based generator with `seed`).  The previous spectral frame, the last 8 blocks and
+ * the low-pass state stay on the device.  pcm must hold sum(pos[i]-pos[i-1]) samples; *n_pcm receives the count
+ * (0 for the very first frame, GriffinLim.py:131-132).  Synchronous. */
+int sgs_gl_node_push(sgs_gl_node* node, const double* logmel, int n, const int32_t* pos, int32_t pos_before,
+                     const double* noise, uint64_t seed, int16_t* pcm, int* n_pcm, void* stream);
+
+/* Dequantization node alone (livenodes/Dequantization.py:15-18; local/quantization.py:125-135 with smooth = 0):
+ * out[r][b] = medians[b][labels[r][b]], optionally smoothed across bins with taps[2*radius+1] ('reflect'). */
+int sgs_dequantize(const double* medians, int n_bins, int n_levels, const double* taps, int radius,
+                   const double* labels, int64_t n_rows, int smooth, double* out, void* stream);
 
 #ifdef __cplusplus
 }

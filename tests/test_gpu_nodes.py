@@ -1,0 +1,125 @@
+"""The livenodes drop-in nodes (streaming device state) and decode.py entry points against reference fixtures."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from sgs import synth
+from helpers import load, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def push(node, data, chunk):
+    for i in range(0, len(data), chunk):
+        node.add_data(np.array(data[i:i + chunk]))
+
+
+@pytest.mark.parametrize('sr', [1024, 2048])
+@pytest.mark.parametrize('ln', [50, 60])
+def test_ecog_feat_calc_node_streaming(sr, ln):
+    from livenodes import ECogFeatCalc
+    G = load('features.npz')
+    x = synth.seeg_session(7, 6, sr, 1.37).astype(np.float64)
+    for chunk_size, push_chunk in ((32, 16), (32, 32), (64, 64), (32, 100)):
+        node = ECogFeatCalc.ECogFeatCalc(sr, 50, 10, 4, 5, line_noise=ln, chunk_size=chunk_size, has_inputs=False)
+        rows = []
+        node.add_output(lambda f: rows.append(np.array(f, copy=True)))
+        push(node, x, push_chunk)
+        g = G['sr%d_ln%d_online_cs%d_p%d' % (sr, ln, chunk_size, push_chunk)]
+        got = np.array(rows)
+        assert got.shape == g.shape
+        assert np.abs(got - g).max() < 1e-9
+
+
+@pytest.fixture(scope='module')
+def model():
+    G = load('train_decode.npz')
+    with open(os.path.join(GOLDEN, 'estimators.pkl'), 'rb') as fh:
+        blob = fh.read()
+    return G, blob
+
+
+def test_node_chain_matches_reference_chain(model):
+    """decode.setup_decoder graph fed in-process with 16-sample chunks == the reference chain's recorded outputs."""
+    import decode
+    from livenodes import Node
+    G, blob = model
+    sr, bad = int(G['sr']), list(G['bad'])
+    test = synth.seeg_session(2, int(G['n_ch']), sr, 3.0).astype(np.float64)
+    src = Node.Node(name='src', has_inputs=False)
+    rec_seeg, rec_spec, rec_audio = decode.setup_decoder(src, sr, blob, G['medians'], bad, G['select'], gl_norm=10,
+                                                         include_soundcard=False)
+    np.random.seed(4001)
+    for i in range(0, len(test), 16):
+        src.output_data(np.array(test[i:i + 16]))
+    spec = np.array(rec_spec.get_data())
+    audio = np.hstack([a for a in rec_audio.get_data() if len(a)])
+    assert np.array_equal(spec, G['dec_spec'])
+    d = np.abs(audio.astype(int) - G['dec_audio'].astype(int))
+    assert audio.shape == G['dec_audio'].shape and d.max() <= 1 and (d > 0).mean() < 1e-3
+    assert np.vstack(rec_seeg.get_data()).shape == test.shape
+
+
+def test_perform_offline_decoding_batched(model):
+    import decode
+    G, blob = model
+    D = load('offline_decoding.npz')
+    sr, bad = int(G['sr']), list(G['bad'])
+    tiny = synth.seeg_session(2, int(G['n_ch']), sr, 3.0).astype(np.float64)[:1024]
+    np.random.seed(4003)
+    spec, audio, rec, sf = decode.perform_offline_decoding((blob, G['medians'], bad, G['select']), tiny, sr, 10)
+    assert sf == sr and rec.shape == tiny.shape
+    assert np.array_equal(spec, D['spec'])
+    assert audio.dtype == np.int16 and audio.shape == D['audio'].shape
+    assert np.abs(audio.astype(int) - D['audio'].astype(int)).max() <= 1
+
+
+FORKED = r"""
+import os, sys, pickle, numpy as np
+root = sys.argv[1]
+sys.path.insert(0, os.path.join(root, 'closed-loop-seeg-speech-synthesis_b200'))
+from sgs import synth
+import decode
+G = np.load(os.path.join(root, 'tests', 'golden', 'train_decode.npz'))
+blob = open(os.path.join(root, 'tests', 'golden', 'estimators.pkl'), 'rb').read()
+sr, bad = int(G['sr']), list(G['bad'])
+tiny = synth.seeg_session(2, int(G['n_ch']), sr, 3.0).astype(np.float64)[:1024]
+np.random.seed(4003)
+# the parent process never touches CUDA: the graph (and its device state) lives in the forked feeder process
+spec, audio, rec, sf = decode.perform_offline_decoding((blob, G['medians'], bad, G['select']), tiny, sr, 10, streaming=True)
+np.savez(sys.argv[2], spec=spec, audio=audio, rec_shape=np.array(rec.shape))
+"""
+
+
+def test_perform_offline_decoding_forked_sender(model, tmp_path):
+    """The reference's own execution model (decode.py:71-96): Sender forks, the whole graph runs in the child,
+    results come back through Manager lists.  Needs a parent without a CUDA context, hence the subprocess."""
+    import subprocess
+    import sys
+    D = load('offline_decoding.npz')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / 'forked.npz')
+    subprocess.run([sys.executable, '-c', FORKED, root, out], check=True, timeout=600)
+    R = np.load(out)
+    assert np.array_equal(R['spec'], D['spec'])
+    assert R['audio'].shape == D['audio'].shape
+    assert np.abs(R['audio'].astype(int) - D['audio'].astype(int)).max() <= 1
+    assert list(R['rec_shape']) == list(D['rec_shape'])
+
+
+def test_dequantize_spectrogram_and_herff():
+    from local.offline import herff2016_b
+    from local.quantization import dequantize_spectrogram, quantize_spectrogram, compute_borders_logistic
+    import oracle as O
+    G = load('train_decode.npz')
+    q = G['q_head'].astype(float)
+    assert np.array_equal(dequantize_spectrogram(q, G['medians']), O.dequantize_spectrogram(q, G['medians']))
+    F = load('features.npz')
+    x = synth.seeg_session(7, 6, 1024, 1.37).astype(np.float64)
+    assert np.abs(herff2016_b(x, 1024) - F['sr1024_ln50_offline']).max() < 1e-9
+    assert np.abs(herff2016_b(x, 1024, line_noise=60, skip_stacking=True) - F['sr1024_ln60_offline_nostack']).max() < 1e-9
+    y = G['y_spec_head']
+    med, borders = compute_borders_logistic(y, 9)
+    assert np.array_equal(quantize_spectrogram(y, borders), O.quantize_spectrogram(y, borders))
