@@ -9,6 +9,37 @@ namespace sgs {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+bool g_prof_on = false;
+struct ProfSpan { int id; cudaEvent_t a, b; };
+static std::vector<ProfSpan> g_spans;
+static cudaEvent_t g_open[kProfCount];
+static double g_prof_ms[kProfCount];
+static unsigned long long g_prof_n[kProfCount];
+static const char* kProfNames[kProfCount] = {"iir_init", "iir_state", "iir_carry", "iir_feat", "stack", "lda", "gl_blocks", "gl_ola",
+                                             "lowpass", "stream", "gl_batch", "logmel", "train"};
+
+void prof_begin(int id, cudaStream_t st) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_open[id] = e;
+}
+void prof_end(int id, cudaStream_t st) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_spans.push_back({id, g_open[id], e});
+}
+static void prof_collect() {
+    for (auto& s : g_spans) {
+        cudaEventSynchronize(s.b);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { g_prof_ms[s.id] += ms; g_prof_n[s.id] += 1; }
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    g_spans.clear();
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -102,6 +133,23 @@ int sgs_init(int device) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     return SGS_OK;
+}
+
+/* Kernel-class timing: enable, run, then read.  name in {iir_init, iir_state, iir_carry, iir_feat, stack, lda, gl_blocks,
+ * gl_ola, lowpass, stream, gl_batch, logmel, train}. */
+int sgs_profile_enable(int on) {
+    sgs::prof_collect();
+    sgs::g_prof_on = on != 0;
+    if (on) for (int i = 0; i < sgs::kProfCount; ++i) { sgs::g_prof_ms[i] = 0; sgs::g_prof_n[i] = 0; }
+    return SGS_OK;
+}
+int sgs_profile_read(const char* name, double* total_ms, unsigned long long* launches) {
+    SGS_ARG(name && total_ms && launches, "NULL argument");
+    sgs::prof_collect();
+    for (int i = 0; i < sgs::kProfCount; ++i)
+        if (strcmp(name, sgs::kProfNames[i]) == 0) { *total_ms = sgs::g_prof_ms[i]; *launches = sgs::g_prof_n[i]; return SGS_OK; }
+    sgs::set_error("unknown kernel class '%s'", name);
+    return SGS_ERR_ARG;
 }
 
 int sgs_synchronize(void* stream) {

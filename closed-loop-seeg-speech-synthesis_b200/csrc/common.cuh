@@ -46,6 +46,18 @@ int stage_out(Staged& s, void* p, size_t bytes, cudaStream_t st);          // al
 int finish_out(Staged& s, cudaStream_t st);                                // D2H if needed (async)
 void release(Staged& s, cudaStream_t st);
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
+enum ProfId { kProfIirInit = 0, kProfIirState, kProfIirCarry, kProfIirFeat, kProfStack, kProfLda, kProfGlBlocks, kProfGlOla,
+              kProfLowpass, kProfStream, kProfGlBatch, kProfLogMel, kProfTrain, kProfCount };
+extern bool g_prof_on;
+void prof_begin(int id, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+struct ProfScope {
+    int id; cudaStream_t st;
+    ProfScope(int i, cudaStream_t s) : id(i), st(s) { if (g_prof_on) prof_begin(id, st); }
+    ~ProfScope() { if (g_prof_on) prof_end(id, st); }
+};
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace sgs

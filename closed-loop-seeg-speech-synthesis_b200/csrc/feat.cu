@@ -313,7 +313,7 @@ template <int NB, bool MONIC, int RING, typename TIn>
 static void run_all(const TIn* x, double* feat, double* slots, const double* phi, bool apply_phi, const long long* bounds,
                     const int* kfirst, const int* starts, const double* zf, const FeatCoefs& cf, const FeatGeom& g,
                     cudaStream_t st) {
-    k_iir_init<NB, TIn><<<ceil_div(g.n_streams, 128), 128, 0, st>>>(x, slots, cf, g);
+    { ProfScope ps(kProfIirInit, st); k_iir_init<NB, TIn><<<ceil_div(g.n_streams, 128), 128, 0, st>>>(x, slots, cf, g); }
     SGS_LAUNCHED();
     const int bx = ceil_div(g.n_streams, kStreamsPerBlock);
     constexpr int hand_bytes = (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
@@ -324,16 +324,22 @@ static void run_all(const TIn* x, double* feat, double* slots, const double* phi
         attr_set = true;
     }
     if (g.n_chunks > 1) {
-        k_iir_stages<NB, MONIC, kModeState, RING, TIn><<<dim3(bx, g.n_chunks - 1), kStages * 32, hand_bytes, st>>>(
-            x, feat, slots, bounds, kfirst, starts, zf, cf, g);
+        {
+            ProfScope ps(kProfIirState, st);
+            k_iir_stages<NB, MONIC, kModeState, RING, TIn><<<dim3(bx, g.n_chunks - 1), kStages * 32, hand_bytes, st>>>(
+                x, feat, slots, bounds, kfirst, starts, zf, cf, g);
+        }
         SGS_LAUNCHED();
         if (apply_phi && g.n_chunks > 2) {
-            k_iir_carry<2 * NB><<<ceil_div(g.n_streams, kThreads), kThreads, 0, st>>>(slots, phi, g.n_chunks, g.n_streams);
+            { ProfScope ps(kProfIirCarry, st); k_iir_carry<2 * NB><<<ceil_div(g.n_streams, kThreads), kThreads, 0, st>>>(slots, phi, g.n_chunks, g.n_streams); }
             SGS_LAUNCHED();
         }
     }
-    k_iir_stages<NB, MONIC, kModeFeat, RING, TIn><<<dim3(bx, g.n_chunks), kStages * 32, feat_bytes, st>>>(
-        x, feat, slots, bounds, kfirst, starts, zf, cf, g);
+    {
+        ProfScope ps(kProfIirFeat, st);
+        k_iir_stages<NB, MONIC, kModeFeat, RING, TIn><<<dim3(bx, g.n_chunks), kStages * 32, feat_bytes, st>>>(
+            x, feat, slots, bounds, kfirst, starts, zf, cf, g);
+    }
     SGS_LAUNCHED();
 }
 
@@ -374,7 +380,7 @@ int stack_run(const double* feat, double* out, int n_sessions, int n_windows, in
               int order, int step, cudaStream_t st) {
     const long long total = (long long)n_sessions * n_rows * n_channels * (order + 1);
     if (total == 0) return SGS_OK;
-    k_stack<<<ceil_div(total, 256), 256, 0, st>>>(feat, out, n_windows, n_channels, n_rows, first_row, order, step, total);
+    { ProfScope ps(kProfStack, st); k_stack<<<ceil_div(total, 256), 256, 0, st>>>(feat, out, n_windows, n_channels, n_rows, first_row, order, step, total); }
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;

@@ -288,7 +288,7 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
     if (!attr) { cudaFuncSetAttribute(k_gl_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     long long want = (n_items + kGlWarps - 1) / kGlWarps;
     const int grid = (int)(want < 148 * 5 * 8 ? want : 148 * 5 * 8);
-    k_gl_blocks<<<grid, kGlWarps * 32, smem, st>>>(logmel, noise, seed, blocks, tab, n_frames, n_mels, first_frame, iters, n_items, ring_base, ring_len);
+    { ProfScope ps(kProfGlBlocks, st); k_gl_blocks<<<grid, kGlWarps * 32, smem, st>>>(logmel, noise, seed, blocks, tab, n_frames, n_mels, first_frame, iters, n_items, ring_base, ring_len); }
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;
@@ -298,8 +298,9 @@ int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, 
                 const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered, int n_sessions, int n_frames,
                 int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st) {
     if (n_out <= 0 || n_frames <= first_frame) return SGS_OK;
-    k_gl_ola<<<dim3(n_frames - first_frame, n_sessions), 192, 0, st>>>(blocks, pos, ola_window, v, n_frames, first_frame, n_out);
+    { ProfScope ps(kProfGlOla, st); k_gl_ola<<<dim3(n_frames - first_frame, n_sessions), 192, 0, st>>>(blocks, pos, ola_window, v, n_frames, first_frame, n_out); }
     SGS_LAUNCHED();
+    ProfScope ps_lp(kProfLowpass, st);
     const long long n_thr = (long long)n_chunks * n_sessions;
     k_lp_state<<<ceil_div(n_thr, 128), 128, 0, st>>>(v, states, c, n_out, chunk, n_chunks, n_sessions);
     SGS_LAUNCHED();

@@ -108,7 +108,7 @@ int lda_run(const double* feat, const double* Wt, const double* bias, const doub
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lda_decode<kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     dim3 grid(ceil_div(g.n_rows, kLdaFrames), n_sessions);
-    k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g);
+    { ProfScope ps(kProfLda, st); k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g); }
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;

@@ -33,6 +33,8 @@ def _declare(lib):
     fn('sgs_device_count', c_int, C.POINTER(c_int))
     fn('sgs_synchronize', c_int, c_void_p)
     fn('sgs_launch_count', C.c_ulonglong)
+    fn('sgs_profile_enable', c_int, c_int)
+    fn('sgs_profile_read', c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong))
     fn('sgs_feat_plan_create', c_int, C.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int)
     fn('sgs_feat_plan_destroy', None, c_void_p)
     fn('sgs_feat_extract', c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_int,
@@ -90,6 +92,17 @@ def ensure_init(device=None):
 
 def launch_count():
     return int(lib().sgs_launch_count())
+
+
+def profile_enable(on=True):
+    check(lib().sgs_profile_enable(int(on)))
+
+
+def profile_read(name):
+    """(total device milliseconds, launches) of one kernel class since profile_enable(True)."""
+    ms, n = C.c_double(0), C.c_ulonglong(0)
+    check(lib().sgs_profile_read(name.encode(), C.byref(ms), C.byref(n)))
+    return ms.value, int(n.value)
 
 
 # ---- pointer helpers --------------------------------------------------------------------------

@@ -35,6 +35,11 @@ int sgs_device_count(int* count);
 int sgs_synchronize(void* stream);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long sgs_launch_count(void);
+/* Per-kernel-class device time, measured with CUDA events on the launching stream (bench.py's roofline leg).
+ * Enable, run, then read: name in {iir_init, iir_state, iir_carry, iir_feat, stack, lda, gl_blocks, gl_ola, lowpass,
+ * stream, gl_batch, logmel, train}. */
+int sgs_profile_enable(int on);
+int sgs_profile_read(const char* name, double* total_ms, unsigned long long* launches);
 
 /* ---------------------------------------------------------------------------------------------------
  * High-gamma feature extraction.
