@@ -23,7 +23,32 @@ int dequantize_run(const double* labels, const double* medians, const double* ta
 int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, double* v, double* states, double* zi,
                 const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered, int n_sessions, int n_frames,
                 int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st);
+struct GlBatchTables { const double* window; const cplx* tw_half; const cplx* tw_full; const int* inv_idx; const double* inv_w; };
+int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int n_utt, int T, int n_mels, int iters,
+                 long long x_len, double* mx, short* pcm, cudaStream_t st);
+int logmel_run(const double* audio, long long n_audio, const double* window, const cplx* tw_half, const cplx* tw_full,
+               const double* mel, int n_mels, long long n_frames, int shift, int pad, double* out, cudaStream_t st);
 }  // namespace sgs
+
+static void make_twiddles(int n, std::vector<sgs::cplx>& half, std::vector<sgs::cplx>& full) {
+    // half[t] = exp(-2 pi i t / (n/2)), t < n/2 ; full[k] = exp(-2 pi i k / n), k <= n/2 ; exact at the quadrant points
+    const double pi = 3.14159265358979323846;
+    const int m = n / 2;
+    half.resize(m); full.resize(m + 1);
+    for (int t = 0; t < m; ++t) half[t] = sgs::cplx{cos(2.0 * pi * t / m), -sin(2.0 * pi * t / m)};
+    for (int k = 0; k <= m; ++k) full[k] = sgs::cplx{cos(2.0 * pi * k / n), -sin(2.0 * pi * k / n)};
+    half[0] = sgs::cplx{1, 0};
+    if (m % 4 == 0) { half[m / 4] = sgs::cplx{0, -1}; half[m / 2] = sgs::cplx{-1, 0}; half[3 * m / 4] = sgs::cplx{0, 1}; }
+    full[0] = sgs::cplx{1, 0}; full[m] = sgs::cplx{-1, 0};
+    if (n % 4 == 0) full[n / 4] = sgs::cplx{0, -1};
+}
+
+struct sgs_gl_batch {
+    int n_mels = 0;
+    double *d_window = nullptr, *d_inv_w = nullptr;
+    sgs::cplx *d_tw_half = nullptr, *d_tw_full = nullptr;
+    int* d_inv_idx = nullptr;
+};
 
 struct sgs_gl_node {
     int n_mels = 0, iterations = 0, first_frame = 1;
@@ -168,6 +193,112 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
     if (d_states) cudaFreeAsync(d_states, st);
     if (d_zi) cudaFreeAsync(d_zi, st);
     release(s_mel, st); release(s_noise, st); release(s_pcm, st); release(s_flt, st); release(s_blk, st);
+    if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+void sgs_gl_batch_destroy(sgs_gl_batch* p) {
+    if (!p) return;
+    cudaFree(p->d_window); cudaFree(p->d_inv_w); cudaFree(p->d_tw_half); cudaFree(p->d_tw_full); cudaFree(p->d_inv_idx);
+    delete p;
+}
+
+int sgs_gl_batch_create(sgs_gl_batch** plan, int win_len, int hop, int n_mels, const double* window, const int32_t* inv_idx,
+                        const double* inv_w) {
+    using namespace sgs;
+    SGS_ARG(plan && window && inv_idx && inv_w, "NULL argument");
+    if (win_len != 800 || hop != 160) {
+        set_error("the batch Griffin-Lim kernel is built for 50 ms windows / 10 ms hop at 16 kHz (800 / 160); got %d / %d", win_len, hop);
+        return SGS_ERR_UNSUPPORTED;
+    }
+    SGS_ARG(n_mels >= 1 && n_mels <= 64, "n_mels must be 1..64");
+    const int bins = win_len / 2 + 1;
+    for (int i = 0; i < bins * 2; ++i) SGS_ARG(inv_idx[i] >= 0 && inv_idx[i] < n_mels, "inverse-mel tap index out of range");
+    sgs_gl_batch* p = new sgs_gl_batch();
+    p->n_mels = n_mels;
+    std::vector<cplx> th, tf;
+    make_twiddles(win_len, th, tf);
+    cudaError_t e = upload((void**)&p->d_window, window, sizeof(double) * win_len);
+    if (e == cudaSuccess) e = upload((void**)&p->d_inv_idx, inv_idx, sizeof(int) * bins * 2);
+    if (e == cudaSuccess) e = upload((void**)&p->d_inv_w, inv_w, sizeof(double) * bins * 2);
+    if (e == cudaSuccess) e = upload((void**)&p->d_tw_half, th.data(), sizeof(cplx) * th.size());
+    if (e == cudaSuccess) e = upload((void**)&p->d_tw_full, tf.data(), sizeof(cplx) * tf.size());
+    if (e != cudaSuccess) { sgs_gl_batch_destroy(p); return cuda_fail(e, "table upload", __FILE__, __LINE__); }
+    *plan = p;
+    return SGS_OK;
+}
+
+int sgs_gl_batch_synthesize(sgs_gl_batch* p, const double* logmel, int n_utt, int n_frames, const double* noise,
+                            int64_t noise_stride, int iterations, int16_t* pcm, double* waveform, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(p && logmel && noise && pcm, "NULL argument");
+    SGS_ARG(n_utt >= 1 && iterations >= 0, "bad arguments");
+    SGS_ARG(n_frames >= 6, "need at least 6 spectral frames (the reference divides by max|x| = 0 below that)");
+    const long long x_len = 160LL * (n_frames - 1) + 800, n_out = 160LL * n_frames;
+    SGS_ARG(noise_stride >= x_len, "noise rows must hold at least %lld samples", x_len);
+    Staged s_mel, s_noise, s_pcm, s_wave;
+    double *d_x = nullptr, *d_mx = nullptr;
+    int rc = stage_in(s_mel, logmel, sizeof(double) * (size_t)n_utt * n_frames * p->n_mels, st);
+    if (rc == SGS_OK) rc = stage_in(s_noise, noise, sizeof(double) * ((size_t)(n_utt - 1) * noise_stride + x_len), st);
+    if (rc == SGS_OK) rc = stage_out(s_pcm, pcm, sizeof(int16_t) * (size_t)n_utt * n_out, st);
+    if (rc == SGS_OK && waveform) rc = stage_out(s_wave, waveform, sizeof(double) * (size_t)n_utt * n_out, st);
+    cudaError_t e = cudaSuccess;
+    if (rc == SGS_OK) {
+        e = cudaMallocAsync((void**)&d_x, sizeof(double) * (size_t)n_utt * x_len, st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_mx, sizeof(double) * n_utt, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(d_x, sizeof(double) * x_len, s_noise.dev, sizeof(double) * noise_stride, sizeof(double) * x_len,
+                                  n_utt, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "scratch", __FILE__, __LINE__);
+    }
+    if (rc == SGS_OK) {
+        GlBatchTables tab{p->d_window, p->d_tw_half, p->d_tw_full, p->d_inv_idx, p->d_inv_w};
+        rc = gl_batch_run((const double*)s_mel.dev, d_x, tab, n_utt, n_frames, p->n_mels, iterations, x_len, d_mx, (short*)s_pcm.dev, st);
+    }
+    if (rc == SGS_OK && waveform) {
+        e = cudaMemcpy2DAsync(s_wave.dev, sizeof(double) * n_out, d_x, sizeof(double) * x_len, sizeof(double) * n_out, n_utt,
+                              cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "waveform copy", __FILE__, __LINE__);
+    }
+    if (rc == SGS_OK) rc = finish_out(s_pcm, st);
+    if (rc == SGS_OK && waveform) rc = finish_out(s_wave, st);
+    const bool sync = s_pcm.host || s_wave.host;
+    if (d_x) cudaFreeAsync(d_x, st);
+    if (d_mx) cudaFreeAsync(d_mx, st);
+    release(s_mel, st); release(s_noise, st); release(s_pcm, st); release(s_wave, st);
+    if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int sgs_logmel(const double* audio, int64_t n_audio, const double* window, int win_len, int shift, const double* mel,
+               int n_bins, int n_mels, int64_t n_frames, double* out, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(audio && window && mel && out, "NULL argument");
+    if (win_len != 256 || n_bins != 129) {
+        set_error("the log-mel kernel is built for 16 ms windows at 16 kHz (256 samples, 129 bins); got %d / %d", win_len, n_bins);
+        return SGS_ERR_UNSUPPORTED;
+    }
+    SGS_ARG(shift >= 1 && shift <= win_len && n_mels >= 1 && n_frames >= 0, "bad arguments");
+    if (n_frames == 0) return SGS_OK;
+    std::vector<cplx> th, tf;
+    make_twiddles(win_len, th, tf);
+    Staged s_a, s_w, s_m, s_th, s_tf, s_o;
+    int rc = stage_in(s_a, audio, sizeof(double) * (size_t)n_audio, st);
+    if (rc == SGS_OK) rc = stage_in(s_w, window, sizeof(double) * win_len, st);
+    if (rc == SGS_OK) rc = stage_in(s_m, mel, sizeof(double) * (size_t)n_bins * n_mels, st);
+    if (rc == SGS_OK) rc = stage_in(s_th, th.data(), sizeof(cplx) * th.size(), st);
+    if (rc == SGS_OK) rc = stage_in(s_tf, tf.data(), sizeof(cplx) * tf.size(), st);
+    if (rc == SGS_OK) rc = stage_out(s_o, out, sizeof(double) * (size_t)n_frames * n_mels, st);
+    if (rc == SGS_OK)
+        rc = logmel_run((const double*)s_a.dev, n_audio, (const double*)s_w.dev, (const cplx*)s_th.dev, (const cplx*)s_tf.dev,
+                        (const double*)s_m.dev, n_mels, n_frames, shift, win_len - shift, (double*)s_o.dev, st);
+    if (rc == SGS_OK) rc = finish_out(s_o, st);
+    // th/tf are pageable host vectors: their H2D copies were staged synchronously, safe to drop
+    release(s_a, st); release(s_w, st); release(s_m, st); release(s_th, st); release(s_tf, st);
+    const bool sync = true;
+    release(s_o, st);
     if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
     return rc;
 }

@@ -105,3 +105,47 @@ class GriffinLimNodeOp:
         if want_blocks:
             out.append(blk[0] if squeeze else blk)
         return out[0] if len(out) == 1 else tuple(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch form (local/offline.py:131-192)
+# ---------------------------------------------------------------------------------------------------------
+_batch_plans = {}
+
+
+def _batch_plan(win_len, hop, n_mels):
+    from .design import MelTables
+    key = (win_len, hop, n_mels)
+    if key not in _batch_plans:
+        _lib.ensure_init()
+        mel = MelTables(int(win_len / 2 + 1), n_mels, 16000)
+        window = np.ascontiguousarray(np.hanning(win_len + 1)[:-1], dtype=np.float64)     # offline.py:148
+        idx = np.ascontiguousarray(mel.inv_idx, dtype=np.int32)
+        w = np.ascontiguousarray(mel.inv_w, dtype=np.float64)
+        h = _lib.c_void_p()
+        _lib.check(_lib.lib().sgs_gl_batch_create(_lib.C.byref(h), win_len, hop, n_mels, _lib.ptr(window), _lib.ptr(idx), _lib.ptr(w)))
+        _batch_plans[key] = h
+    return _batch_plans[key]
+
+
+def griffin_lim_batch(logmel, noise, win_length=0.05, hop_size=0.01, num_iterations=8, want_waveform=False):
+    """logmel (B, T, n_mels), noise (B, >= 160*(T-1)+800) float64, numpy or torch-CUDA.  Returns int16 (B, 160*T)."""
+    win_len = int(win_length * 16000)
+    hop = int(win_len / (win_length / hop_size))
+    is_torch = _lib._is_torch(logmel)
+    B, T, nm = logmel.shape
+    n_out = hop * T
+    if is_torch:
+        import torch
+        logmel = logmel.contiguous(); noise = noise.contiguous()
+        pcm = torch.empty((B, n_out), dtype=torch.int16, device=logmel.device)
+        wave = torch.empty((B, n_out), dtype=torch.float64, device=logmel.device) if want_waveform else None
+    else:
+        logmel = np.ascontiguousarray(logmel, dtype=np.float64)
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        pcm = np.empty((B, n_out), dtype=np.int16)
+        wave = np.empty((B, n_out), dtype=np.float64) if want_waveform else None
+    _lib.check(_lib.lib().sgs_gl_batch_synthesize(_batch_plan(win_len, hop, nm), _lib.ptr(logmel), B, T, _lib.ptr(noise),
+                                                  int(noise.shape[1]), int(num_iterations), _lib.ptr(pcm), _lib.ptr(wave),
+                                                  _lib.current_stream(logmel)))
+    return (pcm, wave) if want_waveform else pcm

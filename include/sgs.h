@@ -150,6 +150,26 @@ int sgs_gl_node_synthesize(sgs_gl_node* node, const double* logmel, int n_sessio
 int sgs_gl_node_push(sgs_gl_node* node, const double* logmel, int n, const int32_t* pos, int32_t pos_before,
                      const double* noise, uint64_t seed, int16_t* pcm, int* n_pcm, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Batch Griffin-Lim (local/offline.py:131-192): 50 ms periodic-Hann windows, 10 ms hop, complex phase projection.
+ * window[800]; inv_idx/inv_w[401][2] = 2-tap form of MelFilterBank(401, n_mels, 16000).melInvMatrix.
+ * logmel[n_utt][n_frames][n_mels]; noise[n_utt] rows `noise_stride` doubles apart, each >= 160*(n_frames-1)+800
+ * samples = the head of the reference's np.random.rand(2*T*401) start.  pcm[n_utt][160*n_frames] =
+ * int16(x / max|x| * 32767); waveform (optional) = the un-scaled float result.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct sgs_gl_batch sgs_gl_batch;
+int sgs_gl_batch_create(sgs_gl_batch** plan, int win_len, int hop, int n_mels, const double* window,
+                        const int32_t* inv_idx, const double* inv_w);
+void sgs_gl_batch_destroy(sgs_gl_batch* plan);
+int sgs_gl_batch_synthesize(sgs_gl_batch* plan, const double* logmel, int n_utt, int n_frames, const double* noise,
+                            int64_t noise_stride, int iterations, int16_t* pcm, double* waveform, void* stream);
+
+/* Audio -> log-mel target (local/offline.py:219-241 as train.py:128 calls it: 16 ms symmetric-Hann windows, 10 ms
+ * shift, win_len - shift zeros in front): out[n_frames][n_mels] = log(|rfft(window * frame)| . mel + 1e-7).
+ * mel[n_bins][n_mels] = MelFilterBank.melMatrix. */
+int sgs_logmel(const double* audio, int64_t n_audio, const double* window, int win_len, int shift, const double* mel,
+               int n_bins, int n_mels, int64_t n_frames, double* out, void* stream);
+
 /* Dequantization node alone (livenodes/Dequantization.py:15-18; local/quantization.py:125-135 with smooth = 0):
  * out[r][b] = medians[b][labels[r][b]], optionally smoothed across bins with taps[2*radius+1] ('reflect'). */
 int sgs_dequantize(const double* medians, int n_bins, int n_levels, const double* taps, int radius,
