@@ -60,6 +60,12 @@ def _declare(lib):
     fn('sgs_gl_batch_destroy', None, c_void_p)
     fn('sgs_gl_batch_synthesize', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p)
     fn('sgs_logmel', c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p)
+    fn('sgs_col_minmax', c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p)
+    fn('sgs_quantize', c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p)
+    fn('sgs_spearman', c_int, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p)
+    fn('sgs_col_means', c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p)
+    fn('sgs_lda_stats', c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+       c_void_p, c_void_p, c_void_p, c_void_p)
     fn('sgs_dequantize', c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p)
     return lib
 

@@ -1,0 +1,112 @@
+"""Training entry points with the reference's signatures (train.py:78-205).
+
+    train(eeg, audio, sfreq_eeg, sfreq_audio, bad_channels, nb_mel_bins=40)
+        -> (x_train[:, select], q_spectrogram, medians, estimators, select)
+
+Feature extraction, the log-mel target, quantisation, Spearman ranking and the LDA statistics run on the device;
+the 40 small eigen-problems are solved on the host and wrapped into scikit-learn LinearDiscriminantAnalysis
+objects (when scikit-learn is importable) so the pickled model is interchangeable with the reference's.
+The 48 kHz -> 16 kHz decimation of the audio (train.py:125) is audio-side preparation and stays scipy's
+(SURVEY.md 8f rank 1); pass sfreq_audio=16000 to skip it."""
+import logging
+import os
+import pickle
+
+import numpy as np
+
+from local.offline import compute_spectrogram, herff2016_b
+from local.quantization import dequantize_spectrogram  # noqa: F401  (re-exported like the reference)
+from local.utils import benchmark
+from sgs import training
+
+logger = logging.getLogger('train.py')
+
+
+@benchmark
+def quantization(y_train, nb_intervals=8):
+    """Quantize the logMel spectrogram."""
+    medians, borders, q_spectrogram = training.quantization(y_train, nb_intervals)
+    for i in range(q_spectrogram.shape[1]):
+        diff = np.setdiff1d(np.arange(0, nb_intervals), q_spectrogram[:, i])
+        if diff.size > 0:
+            logger.info('Spec_bin "{}" misses samples for interval index/indices "{}"'.format(i, str(diff)))
+    return medians, borders, q_spectrogram
+
+
+@benchmark
+def feature_selection(x_train, y_train, nb_feats=150):
+    """Feature selection using rank correlation with the frame-mean of the target."""
+    return training.feature_selection(x_train, y_train, nb_feats)
+
+
+@benchmark
+def train_estimators(estimators, x_train, y_train):
+    """Fits one LDA per mel bin.  Every bin shares x_train, so one pass gathers the sufficient statistics of all
+    40 fits; `estimators` (the caller's un-fitted list) is filled in place like the reference does."""
+    stats = training.distributed_lda_stats(x_train, np.arange(x_train.shape[1]), y_train)
+    fitted = training.fit_from_stats(stats)
+    for mel_bin in range(len(estimators)):
+        estimators[mel_bin] = fitted[mel_bin]
+        if (mel_bin + 1) % 5 == 0:
+            logger.info('{:02d} LDAs fitted so far.'.format(mel_bin + 1))
+
+
+@benchmark
+def compute_features(eeg, sfreq_eeg, audio, audio_sr):
+    x_train = herff2016_b(eeg, sfreq_eeg, 0.05, 0.01)
+    if audio_sr != 16000:
+        from scipy.signal import decimate
+        audio = decimate(audio, int(round(audio_sr / 16000)))
+    y_train = compute_spectrogram(audio, 16000, 0.016, 0.01)
+    return x_train, y_train
+
+
+def train(eeg, audio, sfreq_eeg, sfreq_audio, bad_channels, nb_mel_bins=40):
+    if len(bad_channels) > 0:
+        logger.info('EEG original shape: {} x {}'.format(*eeg.shape))
+        mask = np.ones(eeg.shape[1], bool)
+        mask[bad_channels] = False
+        eeg = eeg[:, mask]
+        logger.info('EEG truncated shape: {} x {}'.format(*eeg.shape))
+    else:
+        logger.info('No bad channels specified.')
+
+    x_train, y_train = compute_features(eeg, sfreq_eeg, audio, sfreq_audio)
+    y_train = y_train[20:-4]          # align the audio frames with the 20-frame context / 50 ms window of the features
+
+    medians, borders, q_spectrogram = quantization(y_train, nb_intervals=9)
+    select = feature_selection(x_train, y_train)
+    x_train = x_train[:, select]
+
+    estimators = [None for _ in range(nb_mel_bins)]
+    y_train = q_spectrogram
+    logger.info('x_train: ' + str(x_train.shape))
+    logger.info('y_train: ' + str(y_train.shape))
+    minimum = min(len(x_train), len(y_train))
+    x_train = x_train[0:minimum, :]
+    y_train = y_train[0:minimum, :]
+    train_estimators(estimators=estimators, x_train=x_train, y_train=y_train)
+    return x_train, y_train, medians, estimators, select
+
+
+def store_training_to_file(config, x_train, y_train, medians, estimators, bad_channels, select):
+    """Writes LDAs.pkl, training_features.npy and params (train.py:171-205).  The reference stores params.h5 with
+    h5py; when h5py is not importable the same four datasets go to params.npz."""
+    base = os.path.join(config['General']['storage_dir'], config['General']['session'])
+    with open(os.path.join(base, 'LDAs.pkl'), 'wb') as fh:
+        pickle.dump(estimators, fh)
+    np.save(os.path.join(base, 'training_features.npy'), x_train)
+    blob = np.void(pickle.dumps(estimators))
+    try:
+        import h5py
+        with h5py.File(os.path.join(base, 'params.h5'), 'w') as hf:
+            hf.create_dataset('bad_channels', data=bad_channels)
+            hf.create_dataset('medians_array', data=medians)
+            hf.create_dataset('estimators', data=blob)
+            hf.create_dataset('select', data=select)
+    except ImportError:
+        np.savez(os.path.join(base, 'params.npz'), bad_channels=np.asarray(bad_channels), medians_array=medians,
+                 estimators=np.frombuffer(blob.tobytes(), dtype=np.uint8), select=select)
+    with open(os.path.join(base, 'train.ini'), 'w') as configfile:
+        config.write(configfile)
+    logger.info('Training completed.')

@@ -175,6 +175,30 @@ int sgs_logmel(const double* audio, int64_t n_audio, const double* window, int w
 int sgs_dequantize(const double* medians, int n_bins, int n_levels, const double* taps, int radius,
                    const double* labels, int64_t n_rows, int smooth, double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Training side (train.py:78-168).
+ * ------------------------------------------------------------------------------------------------- */
+/* Per-column min / max of y[n][ncol] (the logistic borders of local/quantization.py:83-109 are derived from them). */
+int sgs_col_minmax(const double* y, int64_t n, int ncol, double* mn, double* mx, void* stream);
+/* quantize_spectrogram (local/quantization.py:112-122): labels[r][c] = smallest k with y[r][c] <= borders[c][k], else 0. */
+int sgs_quantize(const double* y, int64_t n, int ncol, const double* borders, int n_intervals, double* labels, void* stream);
+/* feature_selection's statistic (train.py:96-109): rho[c] = scipy.stats.spearmanr(x[:, c], mean(y, axis=1)) with
+ * average ranks for ties; colsum[c] = sum(x[:, c]) (the caller zeroes rho where that is ~0).  x rows are row_stride
+ * doubles apart (0 = ncol). */
+int sgs_spearman(const double* x, int64_t n, int ncol, int64_t row_stride, const double* y, int ny, double* rho,
+                 double* colsum, void* stream);
+/* Mean of the selected columns (global centring of the LDA statistics). */
+int sgs_col_means(const double* x, int64_t n, int64_t row_stride, const int32_t* select, int n_features, double* xbar,
+                  void* stream);
+/* Sufficient statistics of LinearDiscriminantAnalysis(solver='svd').fit for all bins at once (train.py:112-118):
+ * with Xc = x[:, select] - xbar: G = Xc^T Xc [F][F], class_sums[bin][class][F] = sum of Xc rows per label,
+ * counts[bin][class].  xbar_in: centre on this vector (multi-GPU: the all-reduced global mean) or NULL to use the
+ * mean of the given rows; xbar receives the vector used.  All four outputs are additive across row shards that
+ * share xbar_in, which is what the NCCL all-reduce of train.py's multi-GPU path sums. */
+int sgs_lda_stats(const double* x, int64_t n, int64_t row_stride, const int32_t* select, int n_features,
+                  const double* labels, int n_bins, int n_classes, const double* xbar_in, double* xbar, double* G,
+                  double* class_sums, double* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
