@@ -180,9 +180,11 @@ class MelTables:
                 tri[i, a:c] = (np.arange(a, c) - a) / float(c - a)
             if e > c:
                 tri[i, c:e] = (e - np.arange(c, e)) / float(e - c)
-        fwd = tri.T.copy()                                   # (spec_size, nb)
+        # no copies between the transposes: numpy's pairwise summation order depends on the memory layout, and the
+        # reference sums the transposed VIEWS (MelFilterBank.py:35-39); a copy changes the column sums by an ulp
+        fwd = tri.transpose()                                # (spec_size, nb)
         fwd = _finite(fwd / _colsum(fwd))
-        inv = fwd.T.copy()                                   # (nb, spec_size)
+        inv = fwd.transpose()                                # (nb, spec_size)
         inv = _finite(inv / _colsum(inv))
         self.spec_size = spec_size
         self.n_mels = nb

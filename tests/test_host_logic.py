@@ -1,0 +1,100 @@
+"""Host-side tables and runtime on CPU: window schedules, mel tables, scan planning, the Node callback runtime."""
+import numpy as np
+import pytest
+
+import oracle as O
+from sgs import design
+from sgs.features import FeatureExtractor
+from helpers import load
+
+
+@pytest.mark.parametrize('sr', [1024, 2048])
+def test_window_tables_match_the_oracle_schedules(sr):
+    p = design.FeaturePlan(sr)
+    n = int(7.3 * sr)
+    starts, wl = p.offline_window_starts(n)
+    assert wl == int(round(0.05 * sr)) and len(starts) == int(np.floor((n - 0.05 * sr) / (0.01 * sr))) + 1
+    assert all(starts[k] == int(round(k * 0.01 * sr)) for k in (0, 1, 23, 48, len(starts) - 1))
+    # online schedule: frame ends of the closed form used by the oracle (FrameBuffer.py:177)
+    usable = (n // 32) * 32
+    ends = p.online_frame_ends(usable)
+    frame_size = int(0.05 * sr)
+    first_ms = frame_size / float(sr) * 1000.0
+    k, e, want = 0, frame_size, []
+    while e <= usable + p.zero_fill:
+        want.append(e); k += 1
+        e = round(((first_ms + k * 10.0) / 1000.0) * float(sr))
+    assert list(ends) == want
+    assert p.frame_size == {1024: 51, 2048: 102}[sr] and p.zero_fill == {1024: 41, 2048: 82}[sr]
+
+
+def test_mel_tables_match_reference_fixture():
+    M = load('mel.npz')
+    for size in (129, 401):
+        t = design.MelTables(size, 40, 16000)
+        assert np.array_equal(t.mel, M['mel_%d' % size]) and np.array_equal(t.inv, M['inv_%d' % size])
+        dense = np.zeros_like(t.inv)
+        for f in range(size):
+            for j in range(2):
+                if t.inv_w[f, j] != 0:
+                    dense[t.inv_idx[f, j], f] = t.inv_w[f, j]
+        assert np.array_equal(dense, t.inv)                  # the 2-tap form loses nothing
+
+
+def test_known_constants():
+    assert np.allclose(design.gaussian_taps(0.5), [2.63865e-4, 0.106450774, 0.786570725, 0.106450774, 2.63865e-4], rtol=1e-5)
+    g = design.GriffinLimNodePlan(16, 10, 16000, 40, 8)
+    assert (g.fft_size, g.hop, g.block_len, g.context_width, g.offsets) == (256, 160, 3, 1, [0, 160])
+    assert len(g.lp_a) == 6 and abs(g.lp_a[1] - 4.87292) < 1e-4 and g.window[0] < 0
+
+
+def test_scan_plan_modes():
+    fe = FeatureExtractor(2048)
+    k, clen, hor, phi = fe.scan_plan(1228800, 4096)
+    assert k == 3 and hor < clen and phi is None and hor % 1024 == 0            # truncated zero-state pass
+    k, clen, hor, phi = fe.scan_plan(307200, 64)
+    assert k > 2 and hor == clen and phi is not None and phi.shape == (48, 48)  # exact carry through Phi
+    assert fe.scan_plan(1400, 6)[0] == 1
+    # Phi by sequential propagation reproduces the zero-input response of the cascade
+    A = fe.transition()
+    s = np.random.default_rng(0).normal(size=48)
+    t = s.copy()
+    for _ in range(clen):
+        t = A @ t
+    assert np.abs(phi @ s - t).max() <= 1e-9 * np.abs(t).max()
+
+
+def test_node_runtime_contract():
+    from livenodes import Node, LambdaNode, ChannelSelector
+    src = Node.Node(name='src', has_inputs=False)
+    sel = ChannelSelector.ChannelSelector(exclude=[1])(src)
+    dbl = LambdaNode.LambdaNode(lambda f: f * 2)(sel)
+    got = []
+    dbl.add_output(got.append)
+    src.output_data(np.arange(6.0).reshape(2, 3))
+    assert np.array_equal(got[0], [[0, 4], [6, 10]])
+    with pytest.raises(ValueError):
+        dbl.set_inputs(src)                                  # input already set
+    with pytest.raises(ValueError):
+        Node.Node(has_inputs=False)(src)                     # module has no inputs
+    sink = Node.Node(has_outputs=False)
+    with pytest.raises(ValueError):
+        sink.add_output(got.append)
+    facade = Node.Node(name='facade')
+    facade.set_passthrough(sel, dbl)
+    assert facade.add_data == sel.add_data and facade.add_output == dbl.add_output
+
+
+def test_framebuffer_framing_matches_oracle_schedule():
+    from livenodes import FrameBuffer
+    fb = FrameBuffer.FrameBuffer(21, 1, 1000, warm_start=True)
+    rows = []
+    fb.add_output(lambda f: rows.append(f.copy()))
+    x = np.arange(1.0, 41.0).reshape(-1, 1)
+    for v in x:
+        fb.add_data(v.reshape(1, 1))
+    assert len(rows) == 40 and rows[0].shape == (21, 1)
+    assert rows[0][-1, 0] == 1.0 and np.all(rows[0][:-1] == 0)          # 20 warm-start zeros then the first sample
+    assert np.array_equal(rows[25][:, 0], np.arange(6.0, 27.0))
+    stacked = np.array([r[::5, 0] for r in rows])
+    assert np.array_equal(stacked, O.stack_online(x)[:, :5])
