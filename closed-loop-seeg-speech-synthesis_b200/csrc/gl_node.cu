@@ -35,9 +35,7 @@ struct GlNodeTables {               // device pointers, built once per node conf
 
 struct GlWarpSmem {
     double x[kBlk];
-    cplx a[kHalf];
-    cplx b[kHalf];
-    double zr[2][kBins + 1];
+    cplx a[2][kHalf];               // one work buffer per STFT frame of the block (stages are read-sync-write-sync)
 };
 
 __device__ __forceinline__ double uniform01(unsigned long long seed, unsigned long long item, unsigned idx) {
@@ -47,6 +45,63 @@ __device__ __forceinline__ double uniform01(unsigned long long seed, unsigned lo
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     z ^= z >> 31;
     return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// fromLogMels for one bin through the 2-tap inverse mel matrix (MelFilterBank.py:82-83), out of line (once per block)
+__device__ __noinline__ double mel_magnitude(const double* lm, const int* inv_idx, const double* inv_w, int bin) {
+    const double w0 = inv_w[bin * 2], w1 = inv_w[bin * 2 + 1];
+    double v = 0.0;
+    if (w0 != 0.0) v = exp(lm[inv_idx[bin * 2]]) * w0;
+    if (w1 != 0.0) v = fma(exp(lm[inv_idx[bin * 2 + 1]]), w1, v);
+    return isfinite(v) ? v : 0.0;                                           // MelFilterBank.makeNormal
+}
+
+// exp(np.angle(re + 1j*im)): kept out of line, it is the bulk of the code and is called 8 times per iteration
+__device__ __noinline__ double exp_angle(double im, double re) { return exp(atan2(im, re)); }
+
+// One Stockham stage of the 128-point transform applied to BOTH work buffers at once (two independent transforms
+// in flight per warp hide the shared-memory latency).  Every lane reads all its inputs, the warp syncs, then
+// writes: a single buffer per transform is enough.
+template <int R, int NS, int SIGN>
+__device__ __forceinline__ void stage2(cplx* __restrict__ a0, cplx* __restrict__ a1, const cplx* __restrict__ tw, int lane) {
+    constexpr int M = kHalf / R, PER = M / 32;
+    cplx v[2][PER][R];
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+        const int j = lane + 32 * p;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { v[0][p][r] = a0[j + r * M]; v[1][p][r] = a1[j + r * M]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+        const int j = lane + 32 * p;
+        const int k = j % NS;
+        if (NS > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                cplx w = tw[r * k * (kHalf / (NS * R))];
+                if (SIGN > 0) w.y = -w.y;
+                v[0][p][r] = cmul(v[0][p][r], w);
+                v[1][p][r] = cmul(v[1][p][r], w);
+            }
+        }
+        Butterfly<R, SIGN>::run(v[0][p]);
+        Butterfly<R, SIGN>::run(v[1][p]);
+        const int j0 = (j / NS) * NS * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) { a0[j0 + q * NS] = v[0][p][q]; a1[j0 + q * NS] = v[1][p][q]; }
+    }
+    __syncwarp();
+}
+
+// Forward transform only, out of line (one copy of the four stages in the instruction cache): the inverse is taken
+// as conj(FFT(conj(Z))), with the conjugations folded into the split before it and the unpack after it.
+__device__ __noinline__ void fft128x2(cplx* a0, cplx* a1, const cplx* tw, int lane) {
+    stage2<4, 1, -1>(a0, a1, tw, lane);
+    stage2<4, 4, -1>(a0, a1, tw, lane);
+    stage2<4, 16, -1>(a0, a1, tw, lane);
+    stage2<2, 64, -1>(a0, a1, tw, lane);
 }
 
 __global__ void __launch_bounds__(kGlWarps * 32)
@@ -66,103 +121,100 @@ k_gl_blocks(const double* __restrict__ logmel, const double* __restrict__ noise,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     GlWarpSmem& ws = ws_all[warp];
     const int per_sess = n_frames - first_frame;                            // blocks per session
+    const double exp_pi = exp_angle(0.0, -1.0);                             // exp(angle(negative real)) = e^pi
+    // bin pairs (k, 128-k) owned by this lane in the two rounds: k = lane (round 0; lane 0 takes the self-pair 64) and
+    // k = lane + 32 (round 1).  DC and Nyquist are purely real and handled by lane 0 without transcendentals.
+    const int kr0 = lane == 0 ? kHalf / 2 : lane, kr1 = lane + 32;
+
+    auto magnitude = [&](const double* lm, int bin) -> double { return mel_magnitude(lm, tab.inv_idx, tab.inv_w, bin); };
+
     for (long long item = (long long)blockIdx.x * kGlWarps + warp; item < n_items; item += (long long)gridDim.x * kGlWarps) {
         const int sess = (int)(item / per_sess);
         const int k = first_frame + (int)(item - (long long)sess * per_sess);
         const long long frame = (long long)sess * n_frames + k;
 
-        // magnitudes S[f][bin] of the two spectral frames k-1, k for the bins this lane owns: lane + 32 q (q < 4), lane 0 also 128
-        double S[2][5];
+        // magnitudes of the two spectral frames k-1, k at this lane's bins: [frame][round][k / 128-k], plus DC / Nyquist
+        double S[2][2][2], Sdc[2], Sny[2];
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
             const double* lm = logmel + (frame - 1 + f) * n_mels;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const int bin = (q < 4) ? lane + 32 * q : kHalf;
-                double v = 0.0;
-                if (q < 4 || lane == 0) {
-                    const double w0 = tab.inv_w[bin * 2], w1 = tab.inv_w[bin * 2 + 1];
-                    if (w0 != 0.0) v = exp(lm[tab.inv_idx[bin * 2]]) * w0;
-                    if (w1 != 0.0) v = fma(exp(lm[tab.inv_idx[bin * 2 + 1]]), w1, v);
-                    if (!isfinite(v)) v = 0.0;                              // MelFilterBank.makeNormal
-                }
-                S[f][q] = v;
-            }
+            S[f][0][0] = magnitude(lm, kr0); S[f][0][1] = magnitude(lm, kHalf - kr0);
+            S[f][1][0] = magnitude(lm, kr1); S[f][1][1] = magnitude(lm, kHalf - kr1);
+            Sdc[f] = magnitude(lm, 0); Sny[f] = magnitude(lm, kHalf);
         }
-        // start waveform
         for (int i = lane; i < kBlk; i += 32)
             ws.x[i] = noise ? noise[frame * kBlk + i] : uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)i);
         __syncwarp();
 
+#pragma unroll 1
         for (int it = 0; it < iters; ++it) {
-            // ---- analysis: both frames read the current x ------------------------------------------------
+            // ---- analysis: window + pack both frames (offsets 0 and 160), forward transforms -------------------
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = lane + 32 * i;
+                const double w0 = s_window[2 * n], w1 = s_window[2 * n + 1];
+                ws.a[0][n] = cplx{ws.x[2 * n] * w0, ws.x[2 * n + 1] * w1};
+                ws.a[1][n] = cplx{ws.x[kHop + 2 * n] * w0, ws.x[kHop + 2 * n + 1] * w1};
+            }
+            __syncwarp();
+            fft128x2(ws.a[0], ws.a[1], s_tw_half, lane);
+            // ---- per bin pair: real-FFT split, Z = S * exp(angle(X)) (real: the reference has no 1j, quirk Q1), and
+            //      the inverse split, written back in place ---------------------------------------------------
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
-                const int o = f * kHop;
+                cplx* a = ws.a[f];
+                const cplx a0 = a[0];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int n = lane + 32 * i;
-                    ws.a[n] = cplx{ws.x[o + 2 * n] * s_window[2 * n], ws.x[o + 2 * n + 1] * s_window[2 * n + 1]};
-                }
-                __syncwarp();
-                fft128<-1>(ws.a, ws.b, s_tw_half, lane);
-                // real-FFT split + magnitude projection: zr = S * exp(angle(X)) (real, quirk Q1)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int kk = lane + 32 * q;
-                    double re, im;
-                    if (kk == 0) {
-                        re = ws.a[0].x + ws.a[0].y;                         // DC: numpy returns imag = +0.0 exactly
-                        im = 0.0;
-                    } else {
-                        const cplx A = ws.a[kk], B = cconj(ws.a[kHalf - kk]);
-                        const cplx d = csub(A, B), w = s_tw_full[kk];
-                        const cplx t = cmul(w, d);                          // e^{-i th}(A - B)
-                        re = 0.5 * (A.x + B.x) + 0.5 * t.y;                 // X = (A+B)/2 - i/2 * t
-                        im = 0.5 * (A.y + B.y) - 0.5 * t.x;
-                    }
-                    ws.zr[f][kk] = S[f][q] * exp(atan2(im, re));
+                for (int r = 0; r < 2; ++r) {
+                    const int kk = r == 0 ? kr0 : kr1, k2 = kHalf - kk;
+                    const cplx A = a[kk], B = a[k2], w = s_tw_full[kk], w2 = s_tw_full[k2];
+                    // X[kk] from (A, conj B), X[k2] from (B, conj A)
+                    const cplx d1 = cplx{A.x - B.x, A.y + B.y}, t1 = cmul(w, d1);
+                    const double re1 = 0.5 * (A.x + B.x) + 0.5 * t1.y, im1 = 0.5 * (A.y - B.y) - 0.5 * t1.x;
+                    const cplx d2 = cplx{B.x - A.x, B.y + A.y}, t2 = cmul(w2, d2);
+                    const double re2 = 0.5 * (B.x + A.x) + 0.5 * t2.y, im2 = 0.5 * (B.y - A.y) - 0.5 * t2.x;
+                    const double z1 = S[f][r][0] * exp_angle(im1, re1);
+                    const double z2 = S[f][r][1] * exp_angle(im2, re2);
+                    // inverse split of a real spectrum: Zin[k] = (z_k + z_{128-k}) + i e^{+i th_k} (z_k - z_{128-k})
+                    const double sm = z1 + z2, df = z1 - z2;
+                    // (stored conjugated: the inverse transform below is conj(FFT(conj(.))))
+                    a[kk] = cplx{fma(w.y, df, sm), -(w.x * df)};
+                    if (k2 != kk) a[k2] = cplx{fma(w2.y, -df, sm), w2.x * df};
                 }
                 if (lane == 0) {
-                    const double re = ws.a[0].x - ws.a[0].y;                // Nyquist, imag = +0.0
-                    ws.zr[f][kHalf] = S[f][4] * exp(atan2(0.0, re));
+                    // DC and Nyquist are real with imag = +0.0 in numpy: angle is 0 or pi
+                    const double xdc = a0.x + a0.y, xny = a0.x - a0.y;
+                    const double zdc = Sdc[f] * ((xdc < 0.0 || (xdc == 0.0 && signbit(xdc))) ? exp_pi : 1.0);
+                    const double zny = Sny[f] * ((xny < 0.0 || (xny == 0.0 && signbit(xny))) ? exp_pi : 1.0);
+                    a[0] = cplx{zdc + zny, -(zdc - zny)};
                 }
-                __syncwarp();
             }
-            // ---- synthesis: overwrite x -------------------------------------------------------------------
+            __syncwarp();
+            fft128x2(ws.a[0], ws.a[1], s_tw_half, lane);
+            // ---- synthesis: x = irfft(Z0) w at 0  (+)  irfft(Z1) w at 160; nothing reaches [416, 480) ---------
+            constexpr double scale = 1.0 / kFft;
+            double r0[4][2], r1[4][2];
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                const int o = f * kHop;
-                // i * e^{+i th} * d = i (cos th + i sin th) d = (-sin th) d + i (cos th) d, with w = (cos th, -sin th):
-                // real part = w.y * d, imag part = w.x * d; the spectra are real, so conj() is the identity
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int kk = lane + 32 * i;
-                    const double A = ws.zr[f][kk], B = ws.zr[f][kHalf - kk];
-                    const cplx w = s_tw_full[kk];
-                    const double d = A - B;
-                    ws.a[kk] = cplx{fma(w.y, d, A + B), w.x * d};
-                }
-                __syncwarp();
-                fft128<+1>(ws.a, ws.b, s_tw_half, lane);
-                constexpr double scale = 1.0 / kFft;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int n = lane + 32 * i;
-                    const double r0 = (ws.a[n].x * scale) * s_window[2 * n];
-                    const double r1 = (ws.a[n].y * scale) * s_window[2 * n + 1];
-                    const int m0 = 2 * n, m1 = 2 * n + 1;
-                    if (f == 0) {
-                        ws.x[m0] = r0;
-                        ws.x[m1] = r1;
-                    } else {
-                        ws.x[kHop + m0] = (m0 < kFft - kHop) ? ws.x[kHop + m0] + r0 : r0;
-                        ws.x[kHop + m1] = (m1 < kFft - kHop) ? ws.x[kHop + m1] + r1 : r1;
-                    }
-                }
-                __syncwarp();
+            for (int i = 0; i < 4; ++i) {
+                const int n = lane + 32 * i;
+                const double w0 = s_window[2 * n], w1 = s_window[2 * n + 1];
+                r0[i][0] = (ws.a[0][n].x * scale) * w0; r0[i][1] = (-ws.a[0][n].y * scale) * w1;
+                r1[i][0] = (ws.a[1][n].x * scale) * w0; r1[i][1] = (-ws.a[1][n].y * scale) * w1;
             }
-            for (int i = kHop + kFft + lane; i < kBlk; i += 32) ws.x[i] = 0.0;      // istft never reaches [416, 480)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                               // frame 0 first: the overlap is (0 + r0) + r1
+                const int n = lane + 32 * i;
+                ws.x[2 * n] = r0[i][0];
+                ws.x[2 * n + 1] = r0[i][1];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = 2 * (lane + 32 * i);
+                ws.x[kHop + m] = (m < kFft - kHop) ? ws.x[kHop + m] + r1[i][0] : r1[i][0];
+                ws.x[kHop + m + 1] = (m + 1 < kFft - kHop) ? ws.x[kHop + m + 1] + r1[i][1] : r1[i][1];
+            }
+            for (int i = kHop + kFft + lane; i < kBlk; i += 32) ws.x[i] = 0.0;
             __syncwarp();
         }
         // batch: one row per (session, frame); streaming: slot of the running frame number in a power-of-two ring
@@ -203,32 +255,32 @@ __global__ void k_gl_ola(const double* __restrict__ blocks, const int* __restric
 constexpr int kLpMaxOrd = 8;
 struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
 
-__device__ __forceinline__ double lp_step(double xin, double (&z)[kLpMaxOrd], const LpCoefs& c) {
+template <int ORD>
+__device__ __forceinline__ double lp_step(double xin, double (&z)[ORD], const LpCoefs& c) {
     const double y = fma(c.b[0], xin, z[0]);
 #pragma unroll
-    for (int i = 0; i < kLpMaxOrd - 1; ++i)
-        if (i < c.ord - 1) z[i] = fma(-c.a[i + 1], y, fma(c.b[i + 1], xin, z[i + 1]));
-#pragma unroll
-    for (int i = 0; i < kLpMaxOrd; ++i)
-        if (i == c.ord - 1) z[i] = fma(-c.a[i + 1], y, c.b[i + 1] * xin);
+    for (int i = 0; i < ORD - 1; ++i) z[i] = fma(-c.a[i + 1], y, fma(c.b[i + 1], xin, z[i + 1]));
+    z[ORD - 1] = fma(-c.a[ORD], y, c.b[ORD] * xin);
     return y;
 }
 
 // pass 1: zero-state end state of each chunk.  thread = (session, chunk)
+template <int ORD>
 __global__ void k_lp_state(const double* __restrict__ v, double* __restrict__ states, const __grid_constant__ LpCoefs c,
                            long long n_out, int chunk, int n_chunks, int n_sessions) {
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= (long long)n_chunks * n_sessions) return;
     const int sess = (int)(id / n_chunks), ci = (int)(id - (long long)sess * n_chunks);
     const long long t0 = (long long)ci * chunk, t1 = (t0 + chunk < n_out) ? t0 + chunk : n_out;
-    double z[kLpMaxOrd];
+    double z[ORD];
 #pragma unroll
-    for (int i = 0; i < kLpMaxOrd; ++i) z[i] = 0.0;
+    for (int i = 0; i < ORD; ++i) z[i] = 0.0;
     const double* p = v + (long long)sess * n_out;
-    for (long long t = t0; t < t1; ++t) lp_step(p[t], z, c);
+#pragma unroll 8
+    for (long long t = t0; t < t1; ++t) lp_step<ORD>(__ldg(p + t), z, c);
     double* o = states + ((long long)sess * n_chunks + ci) * kLpMaxOrd;
 #pragma unroll
-    for (int i = 0; i < kLpMaxOrd; ++i) o[i] = z[i];
+    for (int i = 0; i < kLpMaxOrd; ++i) o[i] = i < ORD ? z[i] : 0.0;
 }
 
 // carry: in place, states[ci] becomes the TRUE state at the START of chunk ci (chunk 0 starts from zi).
@@ -254,6 +306,7 @@ __global__ void k_lp_carry(double* __restrict__ states, const double* __restrict
 }
 
 // pass 2: filter each chunk from its true state; clip, scale, truncate to int16.
+template <int ORD>
 __global__ void k_lp_apply(const double* __restrict__ v, const double* __restrict__ states, short* __restrict__ pcm,
                            double* __restrict__ filtered, const __grid_constant__ LpCoefs c, double norm_div,
                            long long n_out, int chunk, int n_chunks, int n_sessions) {
@@ -261,13 +314,14 @@ __global__ void k_lp_apply(const double* __restrict__ v, const double* __restric
     if (id >= (long long)n_chunks * n_sessions) return;
     const int sess = (int)(id / n_chunks), ci = (int)(id - (long long)sess * n_chunks);
     const long long t0 = (long long)ci * chunk, t1 = (t0 + chunk < n_out) ? t0 + chunk : n_out;
-    double z[kLpMaxOrd];
+    double z[ORD];
     const double* si = states + ((long long)sess * n_chunks + ci) * kLpMaxOrd;
 #pragma unroll
-    for (int i = 0; i < kLpMaxOrd; ++i) z[i] = si[i];
+    for (int i = 0; i < ORD; ++i) z[i] = si[i];
     const double* p = v + (long long)sess * n_out;
+#pragma unroll 8
     for (long long t = t0; t < t1; ++t) {
-        const double y = lp_step(p[t], z, c);
+        const double y = lp_step<ORD>(__ldg(p + t), z, c);
         if (filtered) filtered[(long long)sess * n_out + t] = y;
         double q = y / norm_div;                                // np.clip(y / (normFactor * 1.01), -0.99, 0.99) * 32767
         q = q < -0.99 ? -0.99 : (q > 0.99 ? 0.99 : q);
@@ -302,12 +356,20 @@ int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, 
     SGS_LAUNCHED();
     ProfScope ps_lp(kProfLowpass, st);
     const long long n_thr = (long long)n_chunks * n_sessions;
-    k_lp_state<<<ceil_div(n_thr, 128), 128, 0, st>>>(v, states, c, n_out, chunk, n_chunks, n_sessions);
-    SGS_LAUNCHED();
-    k_lp_carry<<<ceil_div(n_sessions, 32), 32, 0, st>>>(states, phi, zi, c.ord, n_chunks, n_sessions);
-    SGS_LAUNCHED();
-    k_lp_apply<<<ceil_div(n_thr, 128), 128, 0, st>>>(v, states, pcm, filtered, c, norm_div, n_out, chunk, n_chunks, n_sessions);
-    SGS_LAUNCHED();
+#define SGS_LP(ORD)                                                                                              \
+    do {                                                                                                         \
+        k_lp_state<ORD><<<ceil_div(n_thr, 128), 128, 0, st>>>(v, states, c, n_out, chunk, n_chunks, n_sessions); \
+        SGS_LAUNCHED();                                                                                          \
+        k_lp_carry<<<ceil_div(n_sessions, 32), 32, 0, st>>>(states, phi, zi, c.ord, n_chunks, n_sessions);       \
+        SGS_LAUNCHED();                                                                                          \
+        k_lp_apply<ORD><<<ceil_div(n_thr, 128), 128, 0, st>>>(v, states, pcm, filtered, c, norm_div, n_out, chunk, n_chunks, n_sessions); \
+        SGS_LAUNCHED();                                                                                          \
+    } while (0)
+    switch (c.ord) {
+        case 1: SGS_LP(1); break; case 2: SGS_LP(2); break; case 3: SGS_LP(3); break; case 4: SGS_LP(4); break;
+        case 5: SGS_LP(5); break; case 6: SGS_LP(6); break; case 7: SGS_LP(7); break; default: SGS_LP(8); break;
+    }
+#undef SGS_LP
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;
 }
