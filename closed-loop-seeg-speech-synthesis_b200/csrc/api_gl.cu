@@ -21,8 +21,8 @@ int gl_emit_stream_run(const double* block_ring, const double* ola_window, doubl
 int dequantize_run(const double* labels, const double* medians, const double* taps, int radius, int smooth, int n_bins,
                    int n_levels, long long n_rows, double* out, cudaStream_t st);
 int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, double* v, double* states, double* zi,
-                const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered, int n_sessions, int n_frames,
-                int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st);
+                const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered,
+                int n_sessions, int n_frames, int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st);
 struct GlBatchTables { const double* window; const cplx* tw_half; const cplx* tw_full; const int* inv_idx; const double* inv_w; };
 int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int n_utt, int T, int n_mels, int iters,
                  long long x_len, double* mx, short* pcm, cudaStream_t st);
@@ -54,7 +54,7 @@ struct sgs_gl_node {
     int n_mels = 0, iterations = 0, first_frame = 1;
     double norm_div = 1.01;
     sgs::LpCoefs lp;
-    double *d_window = nullptr, *d_ola = nullptr, *d_inv_w = nullptr, *d_phi = nullptr;
+    double *d_window = nullptr, *d_ola = nullptr, *d_inv_w = nullptr, *d_phi = nullptr, *d_phi_sub = nullptr;
     sgs::cplx *d_tw_half = nullptr, *d_tw_full = nullptr;
     int* d_inv_idx = nullptr;
     int lp_chunk = 0;
@@ -76,7 +76,7 @@ extern "C" {
 
 void sgs_gl_node_destroy(sgs_gl_node* n) {
     if (!n) return;
-    cudaFree(n->d_window); cudaFree(n->d_ola); cudaFree(n->d_inv_w); cudaFree(n->d_phi);
+    cudaFree(n->d_window); cudaFree(n->d_ola); cudaFree(n->d_inv_w); cudaFree(n->d_phi); cudaFree(n->d_phi_sub);
     cudaFree(n->d_tw_half); cudaFree(n->d_tw_full); cudaFree(n->d_inv_idx);
     cudaFree(n->d_mel); cudaFree(n->d_ring); cudaFree(n->d_lp); cudaFree(n->d_noise); cudaFree(n->d_pcm);
     delete n;
@@ -85,9 +85,10 @@ void sgs_gl_node_destroy(sgs_gl_node* n) {
 int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len, int context_width, int n_mels,
                        const double* window, const double* ola_window, const int32_t* inv_idx, const double* inv_w,
                        const double* lp_b, const double* lp_a, int lp_order, const double* lp_phi, int lp_chunk,
-                       double norm_div, int iterations) {
+                       const double* lp_phi_sub, double norm_div, int iterations) {
     using namespace sgs;
-    SGS_ARG(node && window && ola_window && inv_idx && inv_w && lp_b && lp_a && lp_phi, "NULL argument");
+    SGS_ARG(node && window && ola_window && inv_idx && inv_w && lp_b && lp_a && lp_phi && lp_phi_sub, "NULL argument");
+    SGS_ARG(lp_chunk == 2048, "lp_chunk must be 2048 (32 sub-chunks of 64 samples)");
     if (fft_size != kFft || hop != kHop || block_len != 3 || context_width != 1) {
         set_error("the node-semantics Griffin-Lim kernel is built for 16 ms frames / 10 ms shift at 16 kHz "
                   "(fft 256, hop 160, block 3, context 1); got fft %d hop %d block %d context %d", fft_size, hop, block_len, context_width);
@@ -117,6 +118,7 @@ int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len,
     if (e == cudaSuccess) e = upload((void**)&n->d_tw_half, th.data(), sizeof(cplx) * kHalf);
     if (e == cudaSuccess) e = upload((void**)&n->d_tw_full, tf.data(), sizeof(cplx) * kBins);
     if (e == cudaSuccess) e = upload((void**)&n->d_phi, lp_phi, sizeof(double) * lp_order * lp_order);
+    if (e == cudaSuccess) e = upload((void**)&n->d_phi_sub, lp_phi_sub, sizeof(double) * lp_order * lp_order);
     for (int i = 0; i < kBlockRing; ++i) { n->ring_pos[i] = 0; n->ring_index[i] = -1; }
     if (e == cudaSuccess) e = cudaMalloc((void**)&n->d_mel, sizeof(double) * (kMaxFramesPerPush + 1) * n_mels);
     if (e == cudaSuccess) e = cudaMalloc((void**)&n->d_ring, sizeof(double) * kBlockRing * kBlk);
@@ -163,7 +165,7 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
         if (!d_blocks) { e = cudaMallocAsync((void**)&d_blocks, sizeof(double) * (size_t)n_sessions * n_frames * kBlk, st); own_blocks = true; }
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_pos, sizeof(int) * n_frames, st);
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_v, sizeof(double) * (size_t)n_sessions * n_out, st);
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_states, sizeof(double) * (size_t)n_sessions * n_chunks * kLpMaxOrd, st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_states, sizeof(double) * 2 * (size_t)n_sessions * n_chunks * kLpMaxOrd, st);
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_zi, sizeof(double) * (size_t)n_sessions * ord, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_pos, positions, sizeof(int) * n_frames, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi_host.data(), sizeof(double) * n_sessions * ord, cudaMemcpyHostToDevice, st);

@@ -264,69 +264,111 @@ __device__ __forceinline__ double lp_step(double xin, double (&z)[ORD], const Lp
     return y;
 }
 
-// pass 1: zero-state end state of each chunk.  thread = (session, chunk)
-template <int ORD>
-__global__ void k_lp_state(const double* __restrict__ v, double* __restrict__ states, const __grid_constant__ LpCoefs c,
-                           long long n_out, int chunk, int n_chunks, int n_sessions) {
-    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= (long long)n_chunks * n_sessions) return;
-    const int sess = (int)(id / n_chunks), ci = (int)(id - (long long)sess * n_chunks);
-    const long long t0 = (long long)ci * chunk, t1 = (t0 + chunk < n_out) ? t0 + chunk : n_out;
+// Low-pass passes: thread = one 2048-sample chunk (exact two-pass scan: zero-state chunk responses, sequential
+// carry with Phi = M^2048, final pass).  A warp owns 32 consecutive chunks of one session and stages them through
+// shared memory 64 samples at a time, so every global access is a fully coalesced 256 B row instead of 32 lanes
+// striding 16 KB apart.
+constexpr int kLpTile = 64, kLpChunk = 2048, kLpWarps = 2;
+
+template <int ORD, bool APPLY>
+__global__ void __launch_bounds__(kLpWarps * 32)
+k_lp_pass(const double* __restrict__ v, const double* __restrict__ start_states, double* __restrict__ end_states,
+          short* __restrict__ pcm, double* __restrict__ filtered, const __grid_constant__ LpCoefs c, double norm_div,
+          long long n_out, int n_chunks, int n_groups /*per session*/) {
+    __shared__ double sm[kLpWarps][32][kLpTile + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sess = blockIdx.y;
+    const int group = blockIdx.x * kLpWarps + warp;
+    if (group >= n_groups) return;
+    const int ci0 = group * 32, ci = ci0 + lane;
+    const bool live = ci < n_chunks;
+    const double* ps = v + (long long)sess * n_out;
+    double (*tile)[kLpTile + 1] = sm[warp];
     double z[ORD];
 #pragma unroll
-    for (int i = 0; i < ORD; ++i) z[i] = 0.0;
-    const double* p = v + (long long)sess * n_out;
+    for (int i = 0; i < ORD; ++i) z[i] = (APPLY && live) ? start_states[((long long)sess * n_chunks + ci) * kLpMaxOrd + i] : 0.0;
+    const long long my_t0 = (long long)ci * kLpChunk;
+    for (int tt = 0; tt < kLpChunk / kLpTile; ++tt) {
+        // stage: row r of the tile = samples [tt*64, tt*64+64) of chunk ci0 + r
+#pragma unroll 4
+        for (int q = 0; q < 64; ++q) {
+            const int row = q >> 1, col = (q & 1) * 32 + lane;
+            const long long t = (long long)(ci0 + row) * kLpChunk + tt * kLpTile + col;
+            tile[row][col] = (t < n_out) ? __ldg(ps + t) : 0.0;
+        }
+        __syncwarp();
+        const long long tbase = my_t0 + tt * kLpTile;
+        if (live && tbase < n_out) {
+            const int cnt = (n_out - tbase) < kLpTile ? (int)(n_out - tbase) : kLpTile;
+            if (cnt == kLpTile) {
 #pragma unroll 8
-    for (long long t = t0; t < t1; ++t) lp_step<ORD>(__ldg(p + t), z, c);
-    double* o = states + ((long long)sess * n_chunks + ci) * kLpMaxOrd;
+                for (int j = 0; j < kLpTile; ++j) {
+                    const double y = lp_step<ORD>(tile[lane][j], z, c);
+                    if (APPLY) tile[lane][j] = y;
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    const double y = lp_step<ORD>(tile[lane][j], z, c);
+                    if (APPLY) tile[lane][j] = y;
+                }
+            }
+        }
+        __syncwarp();
+        if (APPLY) {
+#pragma unroll 4
+            for (int q = 0; q < 64; ++q) {
+                const int row = q >> 1, col = (q & 1) * 32 + lane;
+                const long long t = (long long)(ci0 + row) * kLpChunk + tt * kLpTile + col;
+                if (t < n_out) {
+                    const double y = tile[row][col];
+                    if (filtered) filtered[(long long)sess * n_out + t] = y;
+                    double qv = y / norm_div;                       // np.clip(y / (normFactor * 1.01), -0.99, 0.99) * 32767
+                    qv = qv < -0.99 ? -0.99 : (qv > 0.99 ? 0.99 : qv);
+                    pcm[(long long)sess * n_out + t] = (short)(int)(qv * 32767.0);      // np.int16(): truncation toward zero
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (!APPLY && live) {
+        double* o = end_states + ((long long)sess * n_chunks + ci) * kLpMaxOrd;
 #pragma unroll
-    for (int i = 0; i < kLpMaxOrd; ++i) o[i] = i < ORD ? z[i] : 0.0;
+        for (int i = 0; i < kLpMaxOrd; ++i) o[i] = i < ORD ? z[i] : 0.0;
+    }
 }
 
-// carry: in place, states[ci] becomes the TRUE state at the START of chunk ci (chunk 0 starts from zi).
-// thread = session; phi = A^chunk (ord x ord, row-major).
-__global__ void k_lp_carry(double* __restrict__ states, const double* __restrict__ phi, double* __restrict__ zi,
-                           int ord, int n_chunks, int n_sessions) {
+// carry: start[ci] = true state at the start of chunk ci (start[0] = zi); zi receives the final state.
+// thread = session; e (zero-state chunk responses) and start are separate arrays so the loads pipeline.
+template <int ORD>
+__global__ void k_lp_carry(const double* __restrict__ e, double* __restrict__ start, const double* __restrict__ phi,
+                           double* __restrict__ zi, int n_chunks, int n_sessions) {
     const int sess = blockIdx.x * blockDim.x + threadIdx.x;
     if (sess >= n_sessions) return;
-    double s[kLpMaxOrd];
-    for (int i = 0; i < kLpMaxOrd; ++i) s[i] = (i < ord) ? zi[sess * ord + i] : 0.0;
-    double* st = states + (long long)sess * n_chunks * kLpMaxOrd;
-    for (int ci = 0; ci < n_chunks; ++ci) {
-        double e[kLpMaxOrd], nx[kLpMaxOrd];
-        for (int i = 0; i < kLpMaxOrd; ++i) { e[i] = st[ci * kLpMaxOrd + i]; st[ci * kLpMaxOrd + i] = s[i]; }
-        for (int i = 0; i < kLpMaxOrd; ++i) {
-            double acc = e[i];
-            for (int k = 0; k < ord; ++k) acc = fma(phi[i * ord + k], s[k], acc);
-            nx[i] = (i < ord) ? acc : 0.0;
-        }
-        for (int i = 0; i < kLpMaxOrd; ++i) s[i] = nx[i];
-    }
-    for (int i = 0; i < ord; ++i) zi[sess * ord + i] = s[i];      // final state back to the caller (streaming)
-}
-
-// pass 2: filter each chunk from its true state; clip, scale, truncate to int16.
-template <int ORD>
-__global__ void k_lp_apply(const double* __restrict__ v, const double* __restrict__ states, short* __restrict__ pcm,
-                           double* __restrict__ filtered, const __grid_constant__ LpCoefs c, double norm_div,
-                           long long n_out, int chunk, int n_chunks, int n_sessions) {
-    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= (long long)n_chunks * n_sessions) return;
-    const int sess = (int)(id / n_chunks), ci = (int)(id - (long long)sess * n_chunks);
-    const long long t0 = (long long)ci * chunk, t1 = (t0 + chunk < n_out) ? t0 + chunk : n_out;
-    double z[ORD];
-    const double* si = states + ((long long)sess * n_chunks + ci) * kLpMaxOrd;
+    double s[ORD], P[ORD][ORD];
 #pragma unroll
-    for (int i = 0; i < ORD; ++i) z[i] = si[i];
-    const double* p = v + (long long)sess * n_out;
-#pragma unroll 8
-    for (long long t = t0; t < t1; ++t) {
-        const double y = lp_step<ORD>(__ldg(p + t), z, c);
-        if (filtered) filtered[(long long)sess * n_out + t] = y;
-        double q = y / norm_div;                                // np.clip(y / (normFactor * 1.01), -0.99, 0.99) * 32767
-        q = q < -0.99 ? -0.99 : (q > 0.99 ? 0.99 : q);
-        pcm[(long long)sess * n_out + t] = (short)(int)(q * 32767.0);       // np.int16(): truncation toward zero
+    for (int i = 0; i < ORD; ++i) {
+        s[i] = zi[sess * ORD + i];
+#pragma unroll
+        for (int k = 0; k < ORD; ++k) P[i][k] = phi[i * ORD + k];
     }
+    const double* ep = e + (long long)sess * n_chunks * kLpMaxOrd;
+    double* sp = start + (long long)sess * n_chunks * kLpMaxOrd;
+#pragma unroll 4
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        double nx[ORD];
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) {
+            sp[ci * kLpMaxOrd + i] = s[i];
+            double acc = ep[ci * kLpMaxOrd + i];
+#pragma unroll
+            for (int k = 0; k < ORD; ++k) acc = fma(P[i][k], s[k], acc);
+            nx[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < ORD; ++i) s[i] = nx[i];
+    }
+#pragma unroll
+    for (int i = 0; i < ORD; ++i) zi[sess * ORD + i] = s[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -349,20 +391,26 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
 }
 
 int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, double* v, double* states, double* zi,
-                const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered, int n_sessions, int n_frames,
-                int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st) {
+                const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered,
+                int n_sessions, int n_frames, int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st) {
+    if (chunk != kLpChunk) { set_error("low-pass chunk must be %d samples", kLpChunk); return SGS_ERR_ARG; }
     if (n_out <= 0 || n_frames <= first_frame) return SGS_OK;
     { ProfScope ps(kProfGlOla, st); k_gl_ola<<<dim3(n_frames - first_frame, n_sessions), 192, 0, st>>>(blocks, pos, ola_window, v, n_frames, first_frame, n_out); }
     SGS_LAUNCHED();
     ProfScope ps_lp(kProfLowpass, st);
     const long long n_thr = (long long)n_chunks * n_sessions;
+    // states: [2][sessions][chunks][8] - zero-state chunk responses, then true chunk start states
+    double* e_states = states;
+    double* start_states = states + (size_t)n_sessions * n_chunks * kLpMaxOrd;
+    const int n_groups = ceil_div(n_chunks, 32);
+    const dim3 grid(ceil_div(n_groups, kLpWarps), n_sessions);
 #define SGS_LP(ORD)                                                                                              \
     do {                                                                                                         \
-        k_lp_state<ORD><<<ceil_div(n_thr, 128), 128, 0, st>>>(v, states, c, n_out, chunk, n_chunks, n_sessions); \
+        k_lp_pass<ORD, false><<<grid, kLpWarps * 32, 0, st>>>(v, start_states, e_states, pcm, filtered, c, norm_div, n_out, n_chunks, n_groups); \
         SGS_LAUNCHED();                                                                                          \
-        k_lp_carry<<<ceil_div(n_sessions, 32), 32, 0, st>>>(states, phi, zi, c.ord, n_chunks, n_sessions);       \
+        k_lp_carry<ORD><<<ceil_div(n_sessions, 32), 32, 0, st>>>(e_states, start_states, phi, zi, n_chunks, n_sessions); \
         SGS_LAUNCHED();                                                                                          \
-        k_lp_apply<ORD><<<ceil_div(n_thr, 128), 128, 0, st>>>(v, states, pcm, filtered, c, norm_div, n_out, chunk, n_chunks, n_sessions); \
+        k_lp_pass<ORD, true><<<grid, kLpWarps * 32, 0, st>>>(v, start_states, e_states, pcm, filtered, c, norm_div, n_out, n_chunks, n_groups); \
         SGS_LAUNCHED();                                                                                          \
     } while (0)
     switch (c.ord) {

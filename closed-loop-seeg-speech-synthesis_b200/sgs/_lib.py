@@ -47,7 +47,7 @@ def _declare(lib):
     fn('sgs_lda_decode', c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
        c_int, c_void_p)
     fn('sgs_gl_node_create', c_int, C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-       c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, C.c_double, c_int)
+       c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, C.c_double, c_int)
     fn('sgs_gl_node_destroy', None, c_void_p)
     fn('sgs_gl_node_synthesize', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, C.c_uint64, c_void_p,
        c_void_p, c_void_p, c_void_p, c_void_p)

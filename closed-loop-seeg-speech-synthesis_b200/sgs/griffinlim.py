@@ -38,6 +38,7 @@ class GriffinLimNodeOp:
             b = np.ascontiguousarray(p.lp_b / a0, dtype=np.float64)
             a = np.ascontiguousarray(p.lp_a / a0, dtype=np.float64)
             phi = np.ascontiguousarray(propagate(lowpass_transition(b, a), LP_CHUNK))
+            phi_sub = np.ascontiguousarray(propagate(lowpass_transition(b, a), 64))
             win = np.ascontiguousarray(p.window, dtype=np.float64)
             ola = np.ascontiguousarray(p.ola_window, dtype=np.float64)
             idx = np.ascontiguousarray(p.mel.inv_idx, dtype=np.int32)
@@ -45,7 +46,7 @@ class GriffinLimNodeOp:
             h = _lib.c_void_p()
             _lib.check(_lib.lib().sgs_gl_node_create(
                 _lib.C.byref(h), p.fft_size, p.hop, p.block_len, p.context_width, self.n_mels, _lib.ptr(win), _lib.ptr(ola),
-                _lib.ptr(idx), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a), self.order, _lib.ptr(phi), LP_CHUNK,
+                _lib.ptr(idx), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a), self.order, _lib.ptr(phi), LP_CHUNK, _lib.ptr(phi_sub),
                 float(p.norm_factor * 1.01), p.iterations))
             self._handle = h
         return self._handle

@@ -124,12 +124,13 @@ typedef struct sgs_gl_node sgs_gl_node;
 
 /* window = blackman(fft_size); ola_window = blackman(block_len*hop); inv_idx/inv_w[bins][2] = the (at most two)
  * non-zero entries of MelFilterBank.melInvMatrix per spectral bin; lp_b/lp_a[lp_order+1] = the output low-pass;
- * lp_phi[lp_order^2] = (zero-input DF2T state transition)^lp_chunk for the chunked scan; norm_div = normFactor*1.01.
+ * lp_phi[lp_order^2] = (zero-input DF2T state transition)^lp_chunk and lp_phi_sub = the same ^64 for the two-level
+ * chunked scan (lp_chunk must be 2048); norm_div = normFactor*1.01.
  * Only the configuration decode.py uses is built: fft 256, hop 160, block_len 3, context_width 1. */
 int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len, int context_width, int n_mels,
                        const double* window, const double* ola_window, const int32_t* inv_idx, const double* inv_w,
                        const double* lp_b, const double* lp_a, int lp_order, const double* lp_phi, int lp_chunk,
-                       double norm_div, int iterations);
+                       const double* lp_phi_sub, double norm_div, int iterations);
 void sgs_gl_node_destroy(sgs_gl_node* node);
 
 /* logmel[n_sessions][n_frames][n_mels]; positions[n_frames] = write-head position after each frame (host table:
