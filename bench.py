@@ -129,7 +129,7 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - n0
-    prof = {k: _lib.profile_read(k) for k in ('iir_init', 'iir_state', 'iir_carry', 'iir_feat', 'lda', 'gl_blocks', 'gl_ola', 'lowpass')}
+    prof = {k: _lib.profile_read(k) for k in ('iir_init', 'iir_state', 'iir_carry', 'iir_feat', 'lda_tc', 'lda', 'gl_blocks', 'gl_ola', 'lowpass')}
     _lib.profile_enable(False)
     if sampler is not None:
         sampler.terminate(); sampler.wait()
@@ -209,6 +209,7 @@ def run_ours(args):
                                        "unit": "fp64 op/s", "frac": dp_ops / (iir_ms * 1e-3) / FP64_PEAK if iir_ms > 0 else None,
                                        "peak_source": "measured DFMA/s, tools/pipe_peak.cu"}},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
             "clocks": clocks_summary(clk_path, local),
         }
         line["cpu_baseline"] = cpu_baseline_sample()

@@ -33,15 +33,24 @@ __global__ void __launch_bounds__(kLdaFrames * kLdaWarps)
 k_lda_decode(const double* __restrict__ feat, const double* __restrict__ Wt /*[bin][F][KC]*/,
              const double* __restrict__ bias /*[bin][KC]*/, const double* __restrict__ cls /*[bin][KC]*/,
              const int* __restrict__ select, const double* __restrict__ medians, const double* __restrict__ taps,
-             double* __restrict__ labels, double* __restrict__ spec, int smooth, const LdaGeom g) {
+             double* __restrict__ labels, double* __restrict__ spec, int smooth, const LdaGeom g,
+             const int* __restrict__ list, const int* __restrict__ list_count) {
     extern __shared__ double sm[];
     double* xs = sm;                                   // [F][33]
     double* raw = sm + (size_t)g.n_features * 33;      // [n_bins][33]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sess = blockIdx.y;
-    const int row0 = blockIdx.x * kLdaFrames;
-    const int row = row0 + lane;
-    const bool live = row < g.n_rows;
+    int sess = blockIdx.y;
+    int row = blockIdx.x * kLdaFrames + lane;
+    bool live = row < g.n_rows;
+    if (list) {
+        // exact re-scoring of the frames the tensor-core pass flagged: frame id = session * n_rows + row
+        const int n = *list_count, i = blockIdx.x * kLdaFrames + lane;
+        if (blockIdx.x * kLdaFrames >= n) return;
+        live = i < n;
+        const int id = live ? list[i] : list[n - 1];
+        sess = id / g.n_rows;
+        row = id - sess * g.n_rows;
+    }
     const double* fs = feat + (long long)sess * g.n_windows * g.n_channels;
 
     // gather the selected, stacked features of 32 frames
@@ -100,7 +109,7 @@ k_lda_decode(const double* __restrict__ feat, const double* __restrict__ Wt /*[b
 
 int lda_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select,
             const double* medians, const double* taps, double* labels, double* spec, int smooth, int n_sessions,
-            const LdaGeom& g, cudaStream_t st) {
+            const LdaGeom& g, cudaStream_t st, const int* list, const int* list_count, long long list_cap) {
     if (g.n_rows <= 0) return SGS_OK;
     const size_t smem = sizeof(double) * 33 * ((size_t)g.n_features + g.n_bins);
     if (smem > 200 * 1024) { set_error("too many features (%d) for the LDA kernel", g.n_features); return SGS_ERR_UNSUPPORTED; }
@@ -108,7 +117,8 @@ int lda_run(const double* feat, const double* Wt, const double* bias, const doub
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lda_decode<kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     dim3 grid(ceil_div(g.n_rows, kLdaFrames), n_sessions);
-    { ProfScope ps(kProfLda, st); k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g); }
+    if (list) grid = dim3(ceil_div(list_cap, kLdaFrames), 1);      // blocks past the list length exit at once
+    { ProfScope ps(kProfLda, st); k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g, list, list_count); }
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;

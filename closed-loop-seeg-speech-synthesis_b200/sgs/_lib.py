@@ -46,6 +46,7 @@ def _declare(lib):
     fn('sgs_lda_model_destroy', None, c_void_p)
     fn('sgs_lda_decode', c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
        c_int, c_void_p)
+    fn('sgs_lda_last_rescored', c_int, c_void_p, C.POINTER(c_int))
     fn('sgs_gl_node_create', c_int, C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, C.c_double, c_int)
     fn('sgs_gl_node_destroy', None, c_void_p)

@@ -71,6 +71,12 @@ class LdaDecoder:
         except Exception:
             pass
 
+    def last_rescored(self):
+        """Frames the last tensor-core decode re-scored exactly in fp64 (0 when the fp64 kernel ran alone)."""
+        n = _lib.c_int(0)
+        _lib.check(_lib.lib().sgs_lda_last_rescored(self.handle(), _lib.C.byref(n)))
+        return n.value
+
     def decode(self, feat, order=0, step=1, first_row=0, n_rows=None, smooth=False, want_labels=True, want_spec=True):
         """feat: un-stacked log-power (.., W, C) with (order, step, first_row) describing the stacked view, or
         already stacked rows (.., R, 5C) with order=0.  Returns (labels, spectrogram), each (.., rows, n_bins)."""

@@ -121,3 +121,32 @@ def test_griffinlim_sessions_batch_and_device_noise():
     b = op.synthesize(torch.from_numpy(lm).cuda(), None, seed=1)
     c = op.synthesize(torch.from_numpy(lm).cuda(), None, seed=2)
     assert a.is_cuda and torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_lda_tensor_core_path_equals_fp64(model, monkeypatch):
+    """>= 4096 frames take the tcgen05 split-TF32 scoring + exact fp64 re-scoring of near-ties: labels must equal the
+    pure fp64 kernel's (and sklearn's) everywhere, online and offline stacking, ragged last tile, several sessions."""
+    G, est = model
+    sr, bad = int(G['sr']), list(G['bad'])
+    xs = np.stack([np.delete(synth.seeg_session(30 + s, int(G['n_ch']), sr, 25.3), bad, axis=1) for s in range(2)])
+    fe = FeatureExtractor(sr)
+    lp = fe.log_power(xs, online=True, chunk_size=32)
+    assert lp.shape[0] * lp.shape[1] >= 4096
+    dec = LdaDecoder(est, G['select'], G['medians'])
+    lab_tc, spec_tc = dec.decode(lp, order=4, step=5, first_row=0, smooth=True)
+    rescored = dec.last_rescored()
+    monkeypatch.setenv('SGS_LDA_TC', '0')
+    lab_64, spec_64 = dec.decode(lp, order=4, step=5, first_row=0, smooth=True)
+    monkeypatch.delenv('SGS_LDA_TC')
+    assert np.array_equal(lab_tc, lab_64) and np.array_equal(spec_tc, spec_64)
+    want = O.lda_predict(fe.stack(lp[1], online=True), est, G['select'])
+    assert np.array_equal(lab_tc[1], want)
+    assert 0 <= rescored < 0.25 * lab_tc.shape[0] * lab_tc.shape[1], rescored       # the filter has to actually filter
+    print('tensor-core LDA: %d of %d frames re-scored in fp64' % (rescored, lab_tc.shape[0] * lab_tc.shape[1]))
+    # offline view (first_row = 20) on device-resident input
+    import torch
+    lpo = fe.log_power(torch.from_numpy(xs).cuda())
+    lab_o, _ = dec.decode(lpo, order=4, step=5, first_row=20)
+    monkeypatch.setenv('SGS_LDA_TC', '0')
+    lab_o64, _ = dec.decode(lpo, order=4, step=5, first_row=20)
+    assert torch.equal(lab_o, lab_o64)
