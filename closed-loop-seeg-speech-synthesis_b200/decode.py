@@ -35,13 +35,82 @@ class OfflineDecoder:
         self.lda = LdaDecoder(estimators, np.asarray(select), np.asarray(medians_array))
         self.gl = GriffinLimNodeOp(16, 10, 16000, nb_mel_bins, gl_iterations, 7900, gl_norm)
 
-    def decode(self, eeg, noise=None, seed=0):
+    def decode(self, eeg, noise=None, seed=0, sessions_per_batch=1, pinned_outputs=False):
         """eeg: (T, C) or (S, T, C) with bad channels already removed; numpy or torch-CUDA.
-        Returns (spectrogram (.., F, 40) float64, audio (.., n) int16)."""
-        lp = self.features.log_power(eeg, online=True, chunk_size=self.packet_size)
-        _, spec = self.lda.decode(lp, order=4, step=5, first_row=0, smooth=True, want_labels=False)
-        audio = self.gl.synthesize(spec, noise, seed)
-        return spec, audio
+        Returns (spectrogram (.., F, 40) float64, audio (.., n) int16).
+
+        Host input with several sessions is streamed: while one batch of sessions is being decoded, the next one is
+        copied to the device and the previous results are copied back (two CUDA streams, double-buffered staging).
+        pinned_outputs=True returns views of page-locked result buffers owned by this decoder (valid until the next
+        call) instead of fresh arrays."""
+        from sgs import _lib
+        if _lib._is_torch(eeg) or eeg.ndim == 2 or noise is not None or eeg.shape[0] <= sessions_per_batch:
+            lp = self.features.log_power(eeg, online=True, chunk_size=self.packet_size)
+            _, spec = self.lda.decode(lp, order=4, step=5, first_row=0, smooth=True, want_labels=False)
+            audio = self.gl.synthesize(spec, noise, seed)
+            return spec, audio
+        return self._decode_streamed(eeg, seed, sessions_per_batch, pinned_outputs)
+
+    def _decode_streamed(self, eeg, seed, per_batch, pinned_outputs):
+        import torch
+        from sgs import _lib
+        _lib.ensure_init()
+        S, T, C = eeg.shape
+        if eeg.dtype not in (np.float32, np.float64):
+            eeg = eeg.astype(np.float32)
+        host = torch.from_numpy(np.ascontiguousarray(eeg))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        copy_in, copy_out, compute = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+        stage = [torch.empty((per_batch, T, C), dtype=host.dtype, device=dev) for _ in range(2)]
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+        out_spec = out_audio = None
+        pending = []                                        # (device results, event) kept alive until copied back
+        n_batches = -(-S // per_batch)
+
+        def upload(b):
+            lo, hi = b * per_batch, min(S, (b + 1) * per_batch)
+            with torch.cuda.stream(copy_in):
+                copy_in.wait_event(in_free[b & 1])
+                stage[b & 1][:hi - lo].copy_(host[lo:hi], non_blocking=True)
+                in_ready[b & 1].record(copy_in)
+
+        for e in in_free:
+            e.record(compute)
+        upload(0)
+        for b in range(n_batches):
+            lo, hi = b * per_batch, min(S, (b + 1) * per_batch)
+            if b + 1 < n_batches:
+                upload(b + 1)
+            compute.wait_event(in_ready[b & 1])
+            x = stage[b & 1][:hi - lo]
+            lp = self.features.log_power(x, online=True, chunk_size=self.packet_size)
+            in_free[b & 1].record(compute)                  # the staging buffer may be refilled once the features exist
+            _, spec = self.lda.decode(lp, order=4, step=5, first_row=0, smooth=True, want_labels=False)
+            audio = self.gl.synthesize(spec, None, seed + b)
+            done = torch.cuda.Event()
+            done.record(compute)
+            if out_spec is None:
+                key = (S,) + tuple(spec.shape[1:]) + tuple(audio.shape[1:])
+                if pinned_outputs and getattr(self, '_out_key', None) == key:
+                    out_spec, out_audio = self._out_bufs
+                else:
+                    out_spec = torch.empty((S,) + tuple(spec.shape[1:]), dtype=torch.float64).pin_memory()
+                    out_audio = torch.empty((S,) + tuple(audio.shape[1:]), dtype=torch.int16).pin_memory()
+                    if pinned_outputs:
+                        self._out_key, self._out_bufs = key, (out_spec, out_audio)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(done)
+                out_spec[lo:hi].copy_(spec, non_blocking=True)
+                out_audio[lo:hi].copy_(audio, non_blocking=True)
+                spec.record_stream(copy_out)
+                audio.record_stream(copy_out)
+            pending.append((spec, audio))
+        copy_out.synchronize()
+        compute.synchronize()
+        if pinned_outputs:
+            return out_spec.numpy(), out_audio.numpy()
+        return out_spec.numpy().copy(), out_audio.numpy().copy()
 
 
 def decode_sessions(decoder, eeg_sessions, seed=0):

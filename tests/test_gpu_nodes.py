@@ -123,3 +123,21 @@ def test_dequantize_spectrogram_and_herff():
     y = G['y_spec_head']
     med, borders = compute_borders_logistic(y, 9)
     assert np.array_equal(quantize_spectrogram(y, borders), O.quantize_spectrogram(y, borders))
+
+
+def test_streamed_host_decode_equals_single_call(model):
+    """OfflineDecoder.decode with several host sessions (double-buffered H2D / compute / D2H) == resident decode."""
+    import torch
+    import decode
+    G, blob = model
+    sr, bad = int(G['sr']), list(G['bad'])
+    xs = np.stack([np.delete(synth.seeg_session(40 + s, int(G['n_ch']), sr, 4.0), bad, axis=1) for s in range(3)])
+    dec = decode.OfflineDecoder(blob, G['medians'], G['select'], sr, gl_norm=10, packet_size=32)
+    spec_h, audio_h = dec.decode(xs, None, seed=5)
+    assert isinstance(spec_h, np.ndarray) and audio_h.dtype == np.int16
+    for s in range(3):
+        spec_d, audio_d = dec.decode(torch.from_numpy(xs[s:s + 1]).cuda(), None, seed=5 + s)
+        assert np.array_equal(spec_h[s], spec_d[0].cpu().numpy())
+        assert np.array_equal(audio_h[s], audio_d[0].cpu().numpy())
+    spec_p, audio_p = dec.decode(xs, None, seed=5, pinned_outputs=True)
+    assert np.array_equal(spec_p, spec_h) and np.array_equal(audio_p, audio_h)
