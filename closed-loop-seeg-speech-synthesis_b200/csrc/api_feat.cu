@@ -222,6 +222,40 @@ struct sgs_feat_stream {
     size_t x_cap = 0;
 };
 
+namespace sgs {
+int feat_stream_row_width(const sgs_feat_stream* s) { return s->n_channels * (s->order + 1); }
+
+/* Everything of a push except the read-back: copy the new samples (host or device) into the stream's staging
+ * buffer and launch k_feat_stream; the stacked rows land in d_rows (or the stream's own buffer when NULL). */
+int feat_stream_enqueue(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
+                        const int64_t* frame_index, int n_frames, double* d_rows, cudaStream_t st) {
+    SGS_ARG(s && x && n >= 1, "bad arguments");
+    SGS_ARG(n_frames >= 0 && n_frames <= kMaxFramesPerPush && (n_frames == 0 || (frame_ends && frame_index)), "bad frame schedule");
+    SGS_ARG(n <= 128, "push at most 128 samples per call (got %d)", n);
+    const size_t esz = x_is_f64 ? 8 : 4, bytes = (size_t)n * s->n_channels * esz;
+    if (s->x_cap < bytes) {
+        if (s->d_x) SGS_CUDA(cudaFree(s->d_x));
+        SGS_CUDA(cudaMalloc(&s->d_x, bytes * 2));
+        s->x_cap = bytes * 2;
+    }
+    StreamFrames fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.n = n_frames;
+    for (int q = 0; q < n_frames; ++q) {
+        SGS_ARG(frame_ends[q] <= s->consumed + n && frame_ends[q] > s->consumed - 128, "frame %d does not end inside this push", q);
+        fr.end[q] = frame_ends[q];
+        fr.index[q] = frame_index[q];
+    }
+    SGS_CUDA(cudaMemcpyAsync(s->d_x, x, bytes, cudaMemcpyDefault, st));
+    int rc = feat_stream_run(s->plan->n_biquads, s->d_x, x_is_f64 != 0, n, s->n_channels, s->consumed, s->d_z, s->d_sq, s->d_feat,
+                             s->plan->d_zf, s->plan->zero_fill, s->frame_size, s->order, s->step, d_rows ? d_rows : s->d_out,
+                             s->plan->cf, fr, st);
+    if (rc != SGS_OK) return rc;
+    s->consumed += n;
+    return SGS_OK;
+}
+}  // namespace sgs
+
 extern "C" {
 
 void sgs_feat_stream_destroy(sgs_feat_stream* s) {
@@ -255,28 +289,9 @@ int sgs_feat_stream_push(sgs_feat_stream* s, const void* x, int x_is_f64, int n,
                          const int64_t* frame_index, int n_frames, double* out, void* stream) {
     using namespace sgs;
     cudaStream_t st = (cudaStream_t)stream;
-    SGS_ARG(s && x && n >= 1, "bad arguments");
-    SGS_ARG(n_frames >= 0 && n_frames <= kMaxFramesPerPush && (n_frames == 0 || (frame_ends && frame_index && out)), "bad frame schedule");
-    SGS_ARG(n <= 128, "push at most 128 samples per call (got %d)", n);
-    const size_t esz = x_is_f64 ? 8 : 4, bytes = (size_t)n * s->n_channels * esz;
-    if (s->x_cap < bytes) {
-        if (s->d_x) SGS_CUDA(cudaFree(s->d_x));
-        SGS_CUDA(cudaMalloc(&s->d_x, bytes * 2));
-        s->x_cap = bytes * 2;
-    }
-    StreamFrames fr;
-    memset(&fr, 0, sizeof(fr));
-    fr.n = n_frames;
-    for (int q = 0; q < n_frames; ++q) {
-        SGS_ARG(frame_ends[q] <= s->consumed + n && frame_ends[q] > s->consumed - 128, "frame %d does not end inside this push", q);
-        fr.end[q] = frame_ends[q];
-        fr.index[q] = frame_index[q];
-    }
-    SGS_CUDA(cudaMemcpyAsync(s->d_x, x, bytes, cudaMemcpyHostToDevice, st));
-    int rc = feat_stream_run(s->plan->n_biquads, s->d_x, x_is_f64 != 0, n, s->n_channels, s->consumed, s->d_z, s->d_sq, s->d_feat,
-                             s->plan->d_zf, s->plan->zero_fill, s->frame_size, s->order, s->step, s->d_out, s->plan->cf, fr, st);
+    SGS_ARG(n_frames == 0 || out, "bad frame schedule");
+    int rc = feat_stream_enqueue(s, x, x_is_f64, n, frame_ends, frame_index, n_frames, nullptr, st);
     if (rc != SGS_OK) return rc;
-    s->consumed += n;
     if (n_frames > 0) {
         SGS_CUDA(cudaMemcpyAsync(out, s->d_out, sizeof(double) * (size_t)n_frames * s->n_channels * (s->order + 1), cudaMemcpyDeviceToHost, st));
         SGS_CUDA(cudaStreamSynchronize(st));

@@ -14,7 +14,7 @@ struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
 int gl_blocks_run(const double* logmel, const double* noise, unsigned long long seed, double* blocks, const GlNodeTables& tab,
                   int n_sessions, int n_frames, int n_mels, int first_frame, int iters, long long ring_base, int ring_len,
                   cudaStream_t st);
-constexpr int kMaxFramesPerPush = 16, kBlockRing = 8;
+constexpr int kMaxFramesPerPush = 16, kBlockRing = 32;
 struct EmitFrames { int n; long long index[kMaxFramesPerPush]; int pos[kMaxFramesPerPush]; int prev[kMaxFramesPerPush]; int ring_pos[kBlockRing]; long long ring_index[kBlockRing]; };
 int gl_emit_stream_run(const double* block_ring, const double* ola_window, double* lp_state, short* pcm, const LpCoefs& c,
                        double norm_div, int first_frame, const EmitFrames& fr, cudaStream_t st);
@@ -305,18 +305,20 @@ int sgs_logmel(const double* audio, int64_t n_audio, const double* window, int w
     return rc;
 }
 
-/* Streaming form: feed `n` new spectral frames (host), get the audio the node would have emitted for them. */
-int sgs_gl_node_push(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
-                     uint64_t seed, int16_t* pcm, int* n_pcm, void* stream) {
-    using namespace sgs;
-    cudaStream_t st = (cudaStream_t)stream;
-    SGS_ARG(s && logmel && pos && pcm && n_pcm, "NULL argument");
+}  // extern "C"
+
+namespace sgs {
+/* Everything of a node push except the read-back: logmel / noise may be host or device memory; the int16 hop(s) land in
+ * d_pcm (or the node's own buffer when NULL); *n_pcm = number of samples emitted. */
+int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
+                    uint64_t seed, short* d_pcm, int* n_pcm, cudaStream_t st) {
+    SGS_ARG(s && logmel && pos && n_pcm, "NULL argument");
     SGS_ARG(n >= 1 && n <= kMaxFramesPerPush, "push takes 1..%d frames (got %d)", kMaxFramesPerPush, n);
     const int nm = s->n_mels, first = s->first_frame;
     const long long k0 = s->frames_seen;
     // row 0 of d_mel holds the previous frame; append the new ones behind it
-    SGS_CUDA(cudaMemcpyAsync(s->d_mel + nm, logmel, sizeof(double) * n * nm, cudaMemcpyHostToDevice, st));
-    if (noise) SGS_CUDA(cudaMemcpyAsync(s->d_noise + kBlk, noise, sizeof(double) * n * kBlk, cudaMemcpyHostToDevice, st));
+    SGS_CUDA(cudaMemcpyAsync(s->d_mel + nm, logmel, sizeof(double) * n * nm, cudaMemcpyDefault, st));
+    if (noise) SGS_CUDA(cudaMemcpyAsync(s->d_noise + kBlk, noise, sizeof(double) * n * kBlk, cudaMemcpyDefault, st));
     EmitFrames fr;
     memset(&fr, 0, sizeof(fr));
     int total = 0, prev = pos_before;
@@ -342,13 +344,26 @@ int sgs_gl_node_push(sgs_gl_node* s, const double* logmel, int n, const int32_t*
         rc = gl_blocks_run(s->d_mel, noise ? s->d_noise : nullptr, seed, s->d_ring, tab, 1, n + 1, nm, 1 + skip, s->iterations,
                            k0 - 1, kBlockRing, st);
         if (rc == SGS_OK)
-            rc = gl_emit_stream_run(s->d_ring, s->d_ola, s->d_lp, s->d_pcm, s->lp, s->norm_div, first, fr, st);
-        if (rc == SGS_OK) SGS_CUDA(cudaMemcpyAsync(pcm, s->d_pcm, sizeof(short) * total, cudaMemcpyDeviceToHost, st));
+            rc = gl_emit_stream_run(s->d_ring, s->d_ola, s->d_lp, d_pcm ? d_pcm : s->d_pcm, s->lp, s->norm_div, first, fr, st);
     }
     // the newest frame becomes the "previous" one
     SGS_CUDA(cudaMemcpyAsync(s->d_mel, s->d_mel + (size_t)n * nm, sizeof(double) * nm, cudaMemcpyDeviceToDevice, st));
     s->frames_seen += n;
     *n_pcm = total;
+    return rc;
+}
+}  // namespace sgs
+
+extern "C" {
+
+/* Streaming form: feed `n` new spectral frames (host), get the audio the node would have emitted for them. */
+int sgs_gl_node_push(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
+                     uint64_t seed, int16_t* pcm, int* n_pcm, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(pcm, "NULL argument");
+    int rc = gl_node_enqueue(s, logmel, n, pos, pos_before, noise, seed, nullptr, n_pcm, st);
+    if (rc == SGS_OK && *n_pcm > 0) SGS_CUDA(cudaMemcpyAsync(pcm, s->d_pcm, sizeof(short) * *n_pcm, cudaMemcpyDeviceToHost, st));
     if (rc == SGS_OK) SGS_CUDA(cudaStreamSynchronize(st));
     return rc;
 }

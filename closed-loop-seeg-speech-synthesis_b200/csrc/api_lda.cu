@@ -229,6 +229,29 @@ int sgs_lda_decode(const sgs_lda_model* cm, const double* feat, int n_sessions, 
     return rc;
 }
 
+}  // extern "C"
+
+namespace sgs {
+int lda_model_bins(const sgs_lda_model* m) { return m->n_bins; }
+
+/* Score n_rows already-stacked feature rows resident on the device (the streaming chain): labels and the
+ * dequantised (optionally smoothed) spectrum, fp64 kernel, nothing staged, nothing synchronised. */
+int lda_rows_enqueue(const sgs_lda_model* m, const double* d_rows, int n_rows, int row_width, double* d_labels, double* d_spec,
+                     int smooth, cudaStream_t st) {
+    SGS_ARG(m && d_rows && (d_labels || d_spec) && n_rows >= 1, "bad arguments");
+    SGS_ARG(m->max_col < row_width, "select refers to column %d but frames have %d", m->max_col, row_width);
+    SGS_ARG(!smooth || m->smooth_radius > 0, "model was created without smoothing taps");
+    LdaGeom g;
+    g.n_bins = m->n_bins; g.n_classes = m->n_classes; g.n_features = m->n_features; g.n_levels = m->n_levels;
+    g.n_windows = n_rows; g.n_channels = row_width; g.n_rows = n_rows; g.first_row = 0; g.order = 0; g.step = 1;
+    g.smooth_radius = m->smooth_radius;
+    return lda_run(d_rows, m->d_Wt, m->d_bias, m->d_cls, m->d_select, m->d_medians, m->d_taps, d_labels, d_spec, smooth, 1, g, st,
+                   nullptr, nullptr, 0);
+}
+}  // namespace sgs
+
+extern "C" {
+
 /* Diagnostics: number of frames the last tensor-core decode handed to the exact fp64 re-scoring pass. */
 int sgs_lda_last_rescored(const sgs_lda_model* m, int* n_frames) {
     SGS_ARG(m && n_frames, "NULL argument");

@@ -107,6 +107,73 @@ k_lda_decode(const double* __restrict__ feat, const double* __restrict__ Wt /*[b
     }
 }
 
+// ---- few frames (the streaming nodes): one block per frame, one thread per (bin, class) ---------------------------
+// Same arithmetic per score as k_lda_decode - acc = fma(x_f, W[b][f][k], acc) for f ascending, then + bias, strict
+// argmax in class order - so a frame decodes to the same bits whichever kernel runs; only the mapping differs: the
+// 360 scores of a frame are 360 independent 150-long FMA chains instead of 40 x 9 chains walked by one thread.
+template <int KC>
+__global__ void __launch_bounds__(512)
+k_lda_rows(const double* __restrict__ feat, const double* __restrict__ Wt, const double* __restrict__ bias,
+           const double* __restrict__ cls, const int* __restrict__ select, const double* __restrict__ medians,
+           const double* __restrict__ taps, double* __restrict__ labels, double* __restrict__ spec, int smooth, const LdaGeom g) {
+    extern __shared__ double sm[];
+    double* xs = sm;                                   // [F]
+    double* score = xs + g.n_features;                 // [n_bins][KC]
+    double* raw = score + g.n_bins * KC;               // [n_bins]
+    const int row = blockIdx.x, sess = blockIdx.y;
+    const double* fs = feat + (long long)sess * g.n_windows * g.n_channels;
+    for (int f = threadIdx.x; f < g.n_features; f += blockDim.x) {
+        const int col = select[f];
+        const int c = col / (g.order + 1), tap = col - c * (g.order + 1);
+        const int w = row + g.first_row - (g.order - tap) * g.step;
+        xs[f] = (w >= 0) ? fs[(long long)w * g.n_channels + c] : 0.0;
+    }
+    __syncthreads();
+    const int n_scores = g.n_bins * KC;
+    for (int i = threadIdx.x; i < n_scores; i += blockDim.x) {
+        const int b = i / KC, k = i - b * KC;
+        const double* wb = Wt + (long long)b * g.n_features * KC + k;
+        double acc = 0.0;
+#pragma unroll 10
+        for (int f = 0; f < g.n_features; ++f) acc = fma(xs[f], __ldg(wb + f * KC), acc);
+        score[i] = acc + bias[i];
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < g.n_bins; b += blockDim.x) {
+        int best = 0;
+        double bv = score[b * KC];
+#pragma unroll
+        for (int k = 1; k < KC; ++k) {
+            const double s = score[b * KC + k];
+            if (s > bv) { bv = s; best = k; }
+        }
+        const double lab = cls[b * KC + best];
+        if (labels) labels[((long long)sess * g.n_rows + row) * g.n_bins + b] = lab;
+        int lv = (int)lab;
+        lv = lv < 0 ? 0 : (lv >= g.n_levels ? g.n_levels - 1 : lv);
+        raw[b] = medians[b * g.n_levels + lv];
+    }
+    if (!spec) return;
+    __syncthreads();
+    for (int b = threadIdx.x; b < g.n_bins; b += blockDim.x) {
+        double v = raw[b];
+        if (smooth) {
+            const int R = g.smooth_radius;
+            auto at = [&](int i) {
+                if (i < 0) i = -i - 1;
+                if (i >= g.n_bins) i = 2 * g.n_bins - 1 - i;
+                return raw[i];
+            };
+            double t = __dmul_rn(v, taps[R]);
+            for (int jj = -R; jj < 0; ++jj) t = __dadd_rn(t, __dmul_rn(__dadd_rn(at(b + jj), at(b - jj)), taps[R + jj]));
+            v = t;
+        }
+        spec[((long long)sess * g.n_rows + row) * g.n_bins + b] = v;
+    }
+}
+
+constexpr long long kLdaRowsMax = 256;      // up to this many frames the per-frame kernel has the lower latency
+
 int lda_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select,
             const double* medians, const double* taps, double* labels, double* spec, int smooth, int n_sessions,
             const LdaGeom& g, cudaStream_t st, const int* list, const int* list_count, long long list_cap) {
@@ -114,6 +181,15 @@ int lda_run(const double* feat, const double* Wt, const double* bias, const doub
     const size_t smem = sizeof(double) * 33 * ((size_t)g.n_features + g.n_bins);
     if (smem > 200 * 1024) { set_error("too many features (%d) for the LDA kernel", g.n_features); return SGS_ERR_UNSUPPORTED; }
     if (g.n_classes != kMaxClasses) { set_error("LDA kernel is built for %d classes per bin (got %d)", kMaxClasses, g.n_classes); return SGS_ERR_UNSUPPORTED; }
+    if (!list && (long long)g.n_rows * n_sessions <= kLdaRowsMax) {
+        const int threads = 384;
+        const size_t sm_rows = sizeof(double) * ((size_t)g.n_features + (size_t)g.n_bins * (kMaxClasses + 1));
+        if (sm_rows > 48 * 1024) { set_error("too many features (%d) for the per-frame LDA kernel", g.n_features); return SGS_ERR_UNSUPPORTED; }
+        { ProfScope ps(kProfLda, st); k_lda_rows<kMaxClasses><<<dim3(g.n_rows, n_sessions), threads, sm_rows, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g); }
+        SGS_LAUNCHED();
+        SGS_CUDA(cudaGetLastError());
+        return SGS_OK;
+    }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lda_decode<kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     dim3 grid(ceil_div(g.n_rows, kLdaFrames), n_sessions);

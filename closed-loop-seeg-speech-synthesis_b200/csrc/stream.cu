@@ -106,6 +106,7 @@ int feat_stream_run(int n_biquads, const void* x, bool x_is_f64, int n, int n_ch
                     double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int frame_size, int order, int step,
                     double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st) {
     const int grid = ceil_div(n_channels, 128);
+    ProfScope ps(kProfStream, st);
 #define SGS_LAUNCH(NB, T) k_feat_stream<NB, T><<<grid, 128, 0, st>>>((const T*)x, n, n_channels, t0, z, sq_ring, feat_ring, zf, \
                                                                      zero_fill, frame_size, order, step, out, cf, fr)
     if (n_biquads == 24) { if (x_is_f64) SGS_LAUNCH(24, double); else SGS_LAUNCH(24, float); }
@@ -153,7 +154,7 @@ int dequantize_run(const double* labels, const double* medians, const double* ta
 
 // ---- GriffinLim node: overlap-add of the newest block(s) with the ones still in the ring, low-pass, int16 ----
 constexpr int kBlkLen = 480;
-constexpr int kBlockRing = 8;
+constexpr int kBlockRing = 32;      // >= kMaxFramesPerPush + 4: a push writes all its blocks before the first hop is emitted
 constexpr int kLpMaxOrd = 8;
 struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
 struct EmitFrames {
@@ -196,26 +197,36 @@ k_gl_emit_stream(const double* __restrict__ block_ring /*[kBlockRing][480]*/, co
         }
     }
     __syncthreads();
+    const int total = offs[fr.n];
     if (threadIdx.x == 0) {
+        // the recurrence itself is serial (2 dependent DFMA per sample); everything per-sample around it is not
+        // run at the full width kLpMaxOrd with the coefficients beyond c.ord zero: the extra states stay 0 and the
+        // live ones see the same operations (fma(b, x, 0) == b * x), so the state array stays in registers
         double z[kLpMaxOrd];
+#pragma unroll
         for (int i = 0; i < kLpMaxOrd; ++i) z[i] = (i < c.ord) ? lp_state[i] : 0.0;
-        const int total = offs[fr.n];
         for (int t = 0; t < total; ++t) {
             const double xin = v[t];
             const double y = fma(c.b[0], xin, z[0]);
-            for (int i = 0; i < c.ord - 1; ++i) z[i] = fma(-c.a[i + 1], y, fma(c.b[i + 1], xin, z[i + 1]));
-            z[c.ord - 1] = fma(-c.a[c.ord], y, c.b[c.ord] * xin);
-            double qv = y / norm_div;
-            qv = qv < -0.99 ? -0.99 : (qv > 0.99 ? 0.99 : qv);
-            pcm[t] = (short)(int)(qv * 32767.0);
+#pragma unroll
+            for (int i = 0; i < kLpMaxOrd - 1; ++i) z[i] = fma(-c.a[i + 1], y, fma(c.b[i + 1], xin, z[i + 1]));
+            z[kLpMaxOrd - 1] = fma(-c.a[kLpMaxOrd], y, c.b[kLpMaxOrd] * xin);
+            v[t] = y;
         }
-        for (int i = 0; i < c.ord; ++i) lp_state[i] = z[i];
+#pragma unroll
+        for (int i = 0; i < kLpMaxOrd; ++i) if (i < c.ord) lp_state[i] = z[i];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        double qv = v[t] / norm_div;
+        qv = qv < -0.99 ? -0.99 : (qv > 0.99 ? 0.99 : qv);
+        pcm[t] = (short)(int)(qv * 32767.0);
     }
 }
 
 int gl_emit_stream_run(const double* block_ring, const double* ola_window, double* lp_state, short* pcm, const LpCoefs& c,
                        double norm_div, int first_frame, const EmitFrames& fr, cudaStream_t st) {
-    k_gl_emit_stream<<<1, 192, 0, st>>>(block_ring, ola_window, lp_state, pcm, c, norm_div, first_frame, fr);
+    { ProfScope ps(kProfGlOla, st); k_gl_emit_stream<<<1, 192, 0, st>>>(block_ring, ola_window, lp_state, pcm, c, norm_div, first_frame, fr); }
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;

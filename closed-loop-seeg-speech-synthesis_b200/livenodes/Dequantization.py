@@ -13,8 +13,14 @@ class Dequantization(Node.Node):
         self.c = np.arange(len(self.medians_array))
         self._med = np.ascontiguousarray(medians_array, dtype=np.float64)
         self._taps = np.ascontiguousarray(gaussian_taps(0.5), dtype=np.float64)
+        self._chain = None              # set by sgs.chain.FusedChain
 
     def add_data(self, data_frame, data_id=0):
+        ch = self._chain
+        if ch is not None and data_frame is ch.cur_labels:
+            ch.cur_spec = spec = ch.spec[ch.q].copy()
+            self.output_data(spec)
+            return
         labels = np.ascontiguousarray(np.asarray(data_frame, dtype=np.float64).reshape(1, -1))
         out = np.empty_like(labels)
         _lib.ensure_init()

@@ -20,7 +20,7 @@ MAX_PUSH = 128      # samples per device push (csrc/stream.cu)
 
 class ECogFeatCalc(Node.Node):
     def __init__(self, sample_rate, frame_len_ms, frame_shift_ms, model_order=4, step_size=5,
-                 line_noise=50, warm_start=True, chunk_size=32, has_inputs=True, name='ECogFeatCalc'):
+                 line_noise=50, warm_start=True, chunk_size=32, has_inputs=True, name='ECogFeatCalc', fuse_chain=True):
         super().__init__(name=name, has_inputs=has_inputs)
         if not warm_start:
             raise NotImplementedError("only the warm_start=True configuration used by decode.py is implemented")
@@ -39,6 +39,8 @@ class ECogFeatCalc(Node.Node):
         self.high_gamma_filter = plan.filters[0]
         self.first_harmonic_filter = plan.filters[1]
         self.second_harmonic_filter = plan.filters[2] if plan.n_filters == 3 else None
+        self.fuse_chain = fuse_chain    # run LDASynthesis/Dequantization/GriffinLim below this node in the same device call
+        self._chain = None
         self._stream = None
         self._pending = None            # samples not yet forming a complete chunk_size block (FrameBuffer semantics)
         self._n_channels = None
@@ -57,9 +59,17 @@ class ECogFeatCalc(Node.Node):
         self._stream = h
         self._n_channels = n_channels
         self._out = np.empty((16, n_channels * (self.model_order + 1)), dtype=np.float64)
+        if self.fuse_chain:
+            from sgs import chain
+            nodes = chain.find_chain(self)
+            if nodes is not None:
+                self._chain = chain.FusedChain(self, *nodes)
 
     def reset_buffer(self):
         """Forget all streaming state (the reference re-arms FrameBuffer.reset_buffer per input process)."""
+        if self._chain is not None:
+            self._chain.close()
+            self._chain = None
         if self._stream is not None:
             _lib.lib().sgs_feat_stream_destroy(self._stream)
         self._stream = None
@@ -70,6 +80,8 @@ class ECogFeatCalc(Node.Node):
 
     def __del__(self):
         try:
+            if self._chain is not None:
+                self._chain.close()
             if self._stream is not None:
                 _lib.lib().sgs_feat_stream_destroy(self._stream)
         except Exception:
@@ -108,6 +120,18 @@ class ECogFeatCalc(Node.Node):
             block = np.ascontiguousarray(data[pos:pos + n])
             e = np.asarray(ends, dtype=np.int64)
             k = np.asarray(idx, dtype=np.int64)
+            ch = self._chain
+            if ch is not None:
+                # the whole chain below this node runs in this one call; the nodes emit their share frame by frame
+                ch.push(block, e, k)
+                self._consumed += n
+                pos += n
+                for q in range(len(ends)):
+                    ch.q = q
+                    ch.cur_rows = row = ch.rows[q].copy()
+                    self.output_data(row)
+                ch.cur_rows = ch.cur_labels = ch.cur_spec = None
+                continue
             _lib.check(_lib.lib().sgs_feat_stream_push(self._stream, _lib.ptr(block), int(block.dtype == np.float64), n,
                                                        _lib.ptr(e) if len(ends) else None, _lib.ptr(k) if len(ends) else None,
                                                        len(ends), _lib.ptr(self._out), None))

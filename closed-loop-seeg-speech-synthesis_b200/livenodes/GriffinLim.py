@@ -40,8 +40,33 @@ class GriffinLimSynthesis(Node.Node):
         self.startTime = time.time()
         self.device_noise = device_noise
         self._pcm = np.empty(16 * 192, dtype=np.int16)
+        self._chain = None              # set by sgs.chain.FusedChain
+
+    def _reserve(self, n):
+        """Host bookkeeping of add_data for the next n frames at once (fused chain): write-head positions, the
+        np.random.rand(480) draws in frame order, and which frames emit audio."""
+        prev = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)
+        pos = np.empty(n, dtype=np.int32)
+        emit = [False] * n
+        noise = None if self.device_noise else np.zeros((n, self.blockLen * self.frameShift))
+        for i in range(n):
+            self.framePos += 1
+            self.outputBufferPosMs += self.frameShiftMs
+            pos[i] = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)
+            emit[i] = not (self.framePos < self.blockLen - self.contextWidth)
+            if emit[i] and noise is not None:
+                noise[i] = np.random.rand(self.blockLen * self.frameShift)
+        return pos, prev, noise, emit
 
     def add_data(self, dataFrame, data_id=0):
+        ch = self._chain
+        if ch is not None and dataFrame is ch.cur_spec:
+            q = ch.q
+            if not ch.emit[q]:
+                return np.array([])
+            self.rfc += ch.pcm_hi[q] - ch.pcm_lo[q]
+            self.output_data(ch.pcm[ch.pcm_lo[q]:ch.pcm_hi[q]].copy())
+            return
         frame = np.ascontiguousarray(np.asarray(dataFrame, dtype=np.float64).reshape(1, -1))
         self.framePos += 1
         prev = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)

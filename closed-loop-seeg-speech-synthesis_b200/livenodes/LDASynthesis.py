@@ -17,8 +17,14 @@ class LDASynthesis(Node.Node):
         self.nb_bins = len(self.estimators)
         self.select = select
         self._dec = None
+        self._chain = None              # set by sgs.chain.FusedChain when the feature node above runs the chain
 
     def add_data(self, frame, data_id=0):
+        ch = self._chain
+        if ch is not None and frame is ch.cur_rows:
+            ch.cur_labels = labels = ch.labels[ch.q].copy()
+            self.output_data(labels)
+            return
         frame = np.asarray(frame, dtype=np.float64).reshape((1, -1))
         if self._dec is None:
             # medians are irrelevant for label output; a dummy table keeps the fused kernel's interface

@@ -57,6 +57,10 @@ def _declare(lib):
     fn('sgs_feat_stream_push', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p)
     fn('sgs_gl_node_push', c_int, c_void_p, c_void_p, c_int, c_void_p, C.c_int32, c_void_p, C.c_uint64, c_void_p,
        C.POINTER(c_int), c_void_p)
+    fn('sgs_chain_create', c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_void_p)
+    fn('sgs_chain_destroy', None, c_void_p)
+    fn('sgs_chain_push', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, C.c_int32, c_void_p,
+       C.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_int), c_void_p)
     fn('sgs_gl_batch_create', c_int, C.POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_void_p, c_void_p)
     fn('sgs_gl_batch_destroy', None, c_void_p)
     fn('sgs_gl_batch_synthesize', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p)

@@ -149,11 +149,29 @@ int sgs_gl_node_synthesize(sgs_gl_node* node, const double* logmel, int n_sessio
 
 /* Streaming form (GriffinLimSynthesis.add_data): feed n (1..16) new spectral frames, receive the audio the node
  * emits for them.  pos[n] = write head after each new frame, pos_before = write head before the first of them;
- * noise[n][480] or NULL (counter-based generator with `seed`).  The previous spectral frame, the last 8 blocks and
+ * noise[n][480] or NULL (counter-based generator with `seed`).  The previous spectral frame, the last 32 blocks and
  * the low-pass state stay on the device.  pcm must hold sum(pos[i]-pos[i-1]) samples; *n_pcm receives the count
  * (0 for the very first frame, GriffinLim.py:131-132).  Synchronous. */
 int sgs_gl_node_push(sgs_gl_node* node, const double* logmel, int n, const int32_t* pos, int32_t pos_before,
                      const double* noise, uint64_t seed, int16_t* pcm, int* n_pcm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused streaming chain: the four nodes decode.py:152-183 wires (ECogFeatCalc -> LDASynthesis -> Dequantization ->
+ * GriffinLimSynthesis), driven back to back on one CUDA stream with ONE host<->device round trip per packet of
+ * samples (the 10 ms-frame latency path).  The chain borrows the three streaming handles: their state is the same
+ * state the single-node entry points above advance, so a chain push equals sgs_feat_stream_push + per frame
+ * sgs_lda_decode(smooth) + sgs_gl_node_push, bit for bit.
+ *   x[n][n_channels] host samples (n <= 128); frame_ends / frame_index[n_frames] as for sgs_feat_stream_push;
+ *   gl_pos[n_frames] / gl_pos_before / noise[n_frames][480] / seed as for sgs_gl_node_push.
+ *   rows[n_frames][n_channels*(order+1)], labels[n_frames][n_bins], spec[n_frames][n_bins] (smoothed),
+ *   pcm[sum of hops] and *n_pcm receive what the four nodes emit.  Synchronous when n_frames > 0.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct sgs_chain sgs_chain;
+int sgs_chain_create(sgs_chain** chain, sgs_feat_stream* feat, int n_channels, const sgs_lda_model* lda, sgs_gl_node* gl);
+void sgs_chain_destroy(sgs_chain* chain);
+int sgs_chain_push(sgs_chain* chain, const void* x, int x_is_f64, int n, const int64_t* frame_ends, const int64_t* frame_index,
+                   int n_frames, const int32_t* gl_pos, int32_t gl_pos_before, const double* noise, uint64_t seed,
+                   double* rows, double* labels, double* spec, int16_t* pcm, int* n_pcm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Batch Griffin-Lim (local/offline.py:131-192): 50 ms periodic-Hann windows, 10 ms hop, complex phase projection.

@@ -150,3 +150,47 @@ def test_lda_tensor_core_path_equals_fp64(model, monkeypatch):
     monkeypatch.setenv('SGS_LDA_TC', '0')
     lab_o64, _ = dec.decode(lpo, order=4, step=5, first_row=20)
     assert torch.equal(lab_o, lab_o64)
+
+
+def test_lda_few_frame_kernel_equals_batch_kernel(model):
+    """Up to 256 frames per call run k_lda_rows (one block per frame, the streaming nodes' path), more run
+    k_lda_decode: same score arithmetic, so the same labels and spectrum to the bit whichever runs."""
+    G, est = model
+    dec = LdaDecoder(est, G['select'], G['medians'])
+    feat = G['dec_feat']                                           # 300 stacked rows -> k_lda_decode
+    labels, spec = dec.decode(feat, smooth=True)
+    for lo, hi in ((0, 1), (1, 4), (4, 104), (104, 300)):          # -> k_lda_rows
+        la, sp = dec.decode(np.ascontiguousarray(feat[lo:hi]), smooth=True)
+        assert np.array_equal(la, labels[lo:hi]) and np.array_equal(sp, spec[lo:hi])
+    sr, bad = int(G['sr']), list(G['bad'])
+    x = np.delete(synth.seeg_session(2, int(G['n_ch']), sr, 3.0), bad, axis=1)
+    lp_on = FeatureExtractor(sr).log_power(x, online=True, chunk_size=32)
+    la, sp = dec.decode(lp_on, order=4, step=5, first_row=0, n_rows=40, smooth=True)     # gather incl. rows before the stream start
+    assert np.array_equal(la, G['dec_labels'][:40]) and np.array_equal(sp, G['dec_spec'][:40])
+
+
+@pytest.mark.parametrize('groups', [[3] * 20, [7, 6, 6, 6] * 2 + [10], [16, 16, 16, 12], [1, 2, 16, 1, 13, 16, 11]])
+def test_gl_node_push_many_frames_equals_one_at_a_time(groups):
+    """sgs_gl_node_push with n new frames (all their blocks are synthesised before the first hop is emitted) gives the
+    audio of n single-frame pushes: the block ring must outlive a whole push."""
+    from sgs import _lib
+    rng = np.random.default_rng(0)
+    T = sum(groups)
+    spec = rng.normal(-2, 1.5, size=(T, 40))
+    noise = rng.random((T, 480))
+
+    def run(gs):
+        op = GriffinLimNodeOp(16, 10, 16000, 40, 8, 7900, 10)
+        pos_all = op.positions(T)
+        out, k, prev = [], 0, 0
+        pcm = np.empty(16 * 192, np.int16)
+        for n in gs:
+            n_pcm = _lib.c_int(0)
+            fr, nz, ps = (np.ascontiguousarray(a[k:k + n]) for a in (spec, noise, pos_all))
+            _lib.check(_lib.lib().sgs_gl_node_push(op.handle(), _lib.ptr(fr), n, _lib.ptr(ps), int(prev), _lib.ptr(nz), 0,
+                                                   _lib.ptr(pcm), _lib.C.byref(n_pcm), None))
+            out.append(pcm[:n_pcm.value].copy())
+            prev, k = int(pos_all[k + n - 1]), k + n
+        return np.hstack(out)
+
+    assert np.array_equal(run(groups), run([1] * T))

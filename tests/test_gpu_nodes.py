@@ -141,3 +141,62 @@ def test_streamed_host_decode_equals_single_call(model):
         assert np.array_equal(audio_h[s], audio_d[0].cpu().numpy())
     spec_p, audio_p = dec.decode(xs, None, seed=5, pinned_outputs=True)
     assert np.array_equal(spec_p, spec_h) and np.array_equal(audio_p, audio_h)
+
+
+def _run_graph(model, fused, packet, seconds=2.0, chunk_size=32, tap=False):
+    import decode
+    from livenodes import Node
+    G, blob = model
+    sr, bad = int(G['sr']), list(G['bad'])
+    test = synth.seeg_session(3, int(G['n_ch']), sr, seconds)               # float32 packets, like an amplifier delivers
+    os.environ['SGS_FUSED_CHAIN'] = '1' if fused else '0'
+    try:
+        src = Node.Node(name='src', has_inputs=False)
+        rec_seeg, rec_spec, rec_audio = decode.setup_decoder(src, sr, blob, G['medians'], bad, G['select'], gl_norm=10,
+                                                             packet_size=chunk_size, include_soundcard=False)
+        feat_node = src.output_classes[0].output_classes[0]
+        lda_node = feat_node.output_classes[0]
+        rows, labels = [], []
+        feat_node.add_output(lambda f: rows.append(np.array(f, copy=True)))
+        lda_node.add_output(lambda f: labels.append(np.array(f, copy=True)))
+        np.random.seed(4001)
+        for i in range(0, len(test), packet):
+            src.output_data(np.array(test[i:i + packet]))
+        assert (feat_node._chain is not None) == fused
+    finally:
+        os.environ.pop('SGS_FUSED_CHAIN', None)
+    audio = [a for a in rec_audio.get_data()]
+    return np.array(rows), np.array(labels), np.array(rec_spec.get_data()), audio
+
+
+@pytest.mark.parametrize('packet,chunk_size', [(16, 32), (64, 64), (100, 32), (700, 32)])
+def test_fused_chain_equals_node_by_node(model, packet, chunk_size):
+    """One sgs_chain_push per packet delivers exactly what the four nodes deliver one call at a time: same callbacks,
+    same order, same bits (features, labels, smoothed spectrum, int16 hops incl. the 159/161-sample ones)."""
+    a = _run_graph(model, True, packet, chunk_size=chunk_size)
+    b = _run_graph(model, False, packet, chunk_size=chunk_size)
+    assert len(a[0]) > 150
+    for x, y in zip(a[:3], b[:3]):
+        assert x.shape == y.shape and np.array_equal(x, y)
+    assert len(a[3]) == len(b[3]) and len(a[3]) == len(a[0]) - 1            # the first frame emits no audio (GriffinLim.py:131)
+    assert all(np.array_equal(p, q) for p, q in zip(a[3], b[3]))
+    assert {len(p) for p in a[3]} <= {159, 160, 161}
+
+
+def test_fused_chain_not_used_for_other_wirings(model):
+    """A second consumer between the nodes, or a missing node, keeps the per-node path."""
+    from livenodes import Node, ECogFeatCalc, LDASynthesis, Dequantization, LambdaNode
+    G, blob = model
+    sr = int(G['sr'])
+    n_good = int(G['n_ch']) - len(list(G['bad']))
+    x = synth.seeg_session(3, n_good, sr, 0.5)
+    src = Node.Node(name='src', has_inputs=False)
+    feat = ECogFeatCalc.ECogFeatCalc(sr, 50, 10, 4, 5, chunk_size=32)(src)
+    lda = LDASynthesis.LDASynthesis(blob, select=G['select'])(feat)
+    mid = LambdaNode.LambdaNode(lambda f: f)(lda)                          # not the reference wiring
+    deq = Dequantization.Dequantization(G['medians'])(mid)
+    out = []
+    deq.add_output(out.append)
+    for i in range(0, len(x), 32):
+        src.output_data(np.array(x[i:i + 32]))
+    assert feat._chain is None and len(out) > 30

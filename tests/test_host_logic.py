@@ -98,3 +98,53 @@ def test_framebuffer_framing_matches_oracle_schedule():
     assert np.array_equal(rows[25][:, 0], np.arange(6.0, 27.0))
     stacked = np.array([r[::5, 0] for r in rows])
     assert np.array_equal(stacked, O.stack_online(x)[:, :5])
+
+
+def test_channel_selector_equals_np_delete():
+    from livenodes import ChannelSelector
+    x = np.arange(40.0).reshape(5, 8)
+    for bad in ([], [0], [2, 5], [7, 1, 1], [-1]):
+        got = []
+        sel = ChannelSelector.ChannelSelector(exclude=bad)
+        sel.add_output(got.append)
+        sel.add_data(x)
+        sel.add_data(x[:, :6] if not bad or max(bad) < 6 and min(bad) >= -6 else x)
+        assert np.array_equal(got[0], np.delete(x, bad, axis=1))
+        assert got[0] is not x and not np.shares_memory(got[0], x)      # a fresh array per chunk, as in the reference
+        y = x[:, :6] if not bad or max(bad) < 6 and min(bad) >= -6 else x
+        assert np.array_equal(got[1], np.delete(y, bad, axis=1))
+
+
+def test_receiver_batches_and_flushes():
+    from livenodes import Receiver
+    rec = Receiver.Receiver(flush_interval=3600.0)
+    for i in range(5):
+        rec.add_data(np.full(3, i))
+    assert len(rec.data) == 0                                 # nothing sent to the Manager yet
+    got = rec.get_data()                                      # same-process read hands the batch over first
+    assert [int(g[0]) for g in got] == [0, 1, 2, 3, 4] and len(rec.data) == 5
+    rec.add_data(np.full(3, 5))
+    rec.stop_processing()
+    assert len(rec.data) == 6
+    assert len(rec.get_data(clear=True)) == 6 and rec.get_data() == []
+    eager = Receiver.Receiver(flush_interval=0, perform_timing=True)
+    eager.add_data(1.5)
+    assert len(eager.data) == 1 and eager.get_data()[0][1] == 1.5
+
+
+def _feed_receiver(rec, n):
+    for i in range(n):
+        rec.add_data(i)
+
+
+def test_receiver_flushes_when_a_forked_feeder_exits():
+    """The reference's execution model: frames are appended in a forked child and read by the parent afterwards."""
+    import multiprocessing
+    from livenodes import Receiver
+    rec = Receiver.Receiver(flush_interval=3600.0)
+    rec.add_data(-1)                                           # the parent's own batch must not be replayed by the child
+    ctx = multiprocessing.get_context('fork')
+    p = ctx.Process(target=_feed_receiver, args=(rec, 7))
+    p.start(); p.join()
+    assert p.exitcode == 0
+    assert sorted(rec.get_data()) == [-1, 0, 1, 2, 3, 4, 5, 6]
