@@ -12,6 +12,7 @@
 #include <math.h>
 #include <vector>
 #include <cub/device/device_segmented_radix_sort.cuh>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sgs {
@@ -276,6 +277,10 @@ int col_means_run(const double* x, long long n, long long row_stride, const int*
     return SGS_OK;
 }
 
+bool lda_stats_tc_supported(int nf, int n_bins, int n_classes);
+int lda_stats_tc_run(const double* x, long long n, long long row_stride, const int* select, int nf, const double* labels, int n_bins,
+                     int n_classes, const double* xbar, double* G, double* sums, double* counts, cudaStream_t st);
+
 int lda_stats_run(const double* x, long long n, long long row_stride, const int* select, int nf, const double* labels, int n_bins,
                   int n_classes, double* xbar, double* G, double* sums, double* counts, const double* xbar_in, cudaStream_t st) {
     ProfScope ps(kProfTrain, st);
@@ -294,6 +299,12 @@ int lda_stats_run(const double* x, long long n, long long row_stride, const int*
         SGS_LAUNCHED();
         k_reduce_slices<<<ceil_div(nf, 128), 128, 0, st>>>(p_col, nf, n_slices, 1.0 / (double)n, xbar);
         SGS_LAUNCHED();
+    }
+    const char* env_tc = getenv("SGS_TRAIN_TC");
+    if (lda_stats_tc_supported(nf, n_bins, n_classes) && !(env_tc && env_tc[0] == '0')) {
+        // tensor-core path (train_tc.cu): exact integer GEMMs on int8 digit matrices
+        cudaFreeAsync(p_col, st); cudaFreeAsync(p_g, st); cudaFreeAsync(p_s, st); cudaFreeAsync(p_c, st);
+        return lda_stats_tc_run(x, n, row_stride, select, nf, labels, n_bins, n_classes, xbar, G, sums, counts, st);
     }
     SGS_CUDA(cudaMemsetAsync(p_g, 0, sizeof(double) * (size_t)n_slices * nf * nf, st));
     k_gram_partial<<<dim3(nt, nt, n_slices), dim3(32, 32), 0, st>>>(x, select, xbar, n, row_stride, nf, n_slices, p_g);

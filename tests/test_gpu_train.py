@@ -83,3 +83,53 @@ def test_lda_stats_shards_are_additive():
     assert np.abs(a['G'] + b['G'] - full['G']).max() < 1e-9
     assert np.array_equal(a['counts'] + b['counts'], full['counts'])
     assert np.abs(a['sums'] + b['sums'] - full['sums']).max() < 1e-9
+
+
+def _exact_stats(X, sel, lab, xbar, n_classes=9):
+    """The statistics the tensor-core path promises, in exact integer arithmetic: Gram matrix and class sums of the
+    46-bit fixed-point quantisation of Xc = X[:, sel] - xbar (Python ints never round)."""
+    Xc = X[:, sel] - xbar
+    amax = np.abs(Xc).max(0)
+    e = np.array([np.frexp(a)[1] if a > 0 else 0 for a in amax])
+    q = np.rint(Xc * np.ldexp(1.0, 46 - e)).astype(np.int64)
+    qo = q.astype(object)
+    G = (qo.T @ qo)
+    scale = np.ldexp(1.0, e - 46)
+    G = np.array([[float(G[i, j]) for j in range(len(sel))] for i in range(len(sel))]) * np.outer(scale, scale)
+    nb = lab.shape[1]
+    sums = np.zeros((nb, n_classes, len(sel)))
+    for b in range(nb):
+        for k in range(n_classes):
+            rows = lab[:, b] == k
+            if rows.any():
+                sums[b, k] = np.array([float(v) for v in qo[rows].sum(0)]) * scale
+    return G, sums
+
+
+@pytest.mark.parametrize('n,nf,nb', [(700, 150, 40), (5000, 25, 6), (129, 160, 42), (70000, 33, 3)])
+def test_lda_stats_tensor_core_is_exact(n, nf, nb, monkeypatch):
+    """tcgen05 kind::i8 digit GEMMs (train_tc.cu) == exact integer Gram / class sums of the quantised data, bit for bit
+    up to the final fp64 summation of 11 terms; and within fp64 round-off of the CUDA-core fp64 kernels."""
+    rng = np.random.default_rng(n)
+    width = max(nf + 10, 48)
+    X = rng.normal(9.0, 0.5, (n, width)) * rng.uniform(0.2, 3.0, width)
+    X[:, 3] = 7.25                                            # a constant column (zero variance) must not break the scaling
+    lab = rng.integers(0, 9, (n, nb)).astype(float)
+    lab[:, 0] = rng.choice([2.0, 7.0], n)                     # a bin that never sees most classes
+    sel = rng.permutation(width)[:nf]
+    tc = training.lda_stats(X, sel, lab)
+    monkeypatch.setenv('SGS_TRAIN_TC', '0')
+    ref = training.lda_stats(X, sel, lab)
+    monkeypatch.delenv('SGS_TRAIN_TC')
+    assert np.array_equal(tc['xbar'], ref['xbar']) and np.array_equal(tc['counts'], ref['counts'])
+    scale = np.abs(ref['G']).max()
+    assert np.abs(tc['G'] - ref['G']).max() <= 1e-11 * scale
+    assert np.abs(tc['sums'] - ref['sums']).max() <= 1e-11 * max(1.0, np.abs(ref['sums']).max())
+    assert np.array_equal(tc['G'], tc['G'].T)                 # integer accumulation: symmetric to the bit
+    if n <= 5000:
+        Gx, Sx = _exact_stats(X, sel, lab, tc['xbar'])
+        assert np.abs(tc['G'] - Gx).max() <= 4e-16 * scale * 11
+        assert np.abs(tc['sums'] - Sx).max() <= 4e-16 * max(1.0, np.abs(Sx).max()) * 6
+    # bit-reproducible run to run (integer atomics commute)
+    again = training.lda_stats(X, sel, lab)
+    assert np.array_equal(again['G'], tc['G']) and np.array_equal(again['sums'], tc['sums'])
