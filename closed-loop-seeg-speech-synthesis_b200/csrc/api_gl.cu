@@ -64,6 +64,11 @@ struct sgs_gl_node {
     long long frames_seen = 0;
     int ring_pos[sgs::kBlockRing];
     long long ring_index[sgs::kBlockRing];
+    // cached write-head table of sgs_gl_node_synthesize (re-uploaded only when the caller's table changes: a copy of this
+    // size goes through the H2D copy engine and would queue behind a concurrent bulk upload on another stream)
+    std::vector<int32_t> h_pos;
+    int* d_pos = nullptr;
+    size_t d_pos_cap = 0;
 };
 
 static cudaError_t upload(void** dst, const void* src, size_t bytes) {
@@ -78,7 +83,7 @@ void sgs_gl_node_destroy(sgs_gl_node* n) {
     if (!n) return;
     cudaFree(n->d_window); cudaFree(n->d_ola); cudaFree(n->d_inv_w); cudaFree(n->d_phi); cudaFree(n->d_phi_sub);
     cudaFree(n->d_tw_half); cudaFree(n->d_tw_full); cudaFree(n->d_inv_idx);
-    cudaFree(n->d_mel); cudaFree(n->d_ring); cudaFree(n->d_lp); cudaFree(n->d_noise); cudaFree(n->d_pcm);
+    cudaFree(n->d_mel); cudaFree(n->d_ring); cudaFree(n->d_lp); cudaFree(n->d_noise); cudaFree(n->d_pcm); cudaFree(n->d_pos);
     delete n;
 }
 
@@ -149,7 +154,18 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
     const int ord = n->lp.ord;
 
     Staged s_mel, s_noise, s_pcm, s_flt, s_blk;
-    int* d_pos = nullptr;
+    if (n->h_pos.size() != (size_t)n_frames || memcmp(n->h_pos.data(), positions, sizeof(int32_t) * n_frames) != 0) {
+        if (n->d_pos_cap < (size_t)n_frames) {
+            SGS_CUDA(cudaStreamSynchronize(st));
+            if (n->d_pos) SGS_CUDA(cudaFree(n->d_pos));
+            n->d_pos = nullptr; n->d_pos_cap = 0; n->h_pos.clear();
+            SGS_CUDA(cudaMalloc((void**)&n->d_pos, sizeof(int32_t) * n_frames));
+            n->d_pos_cap = n_frames;
+        }
+        n->h_pos.assign(positions, positions + n_frames);
+        SGS_CUDA(cudaMemcpyAsync(n->d_pos, n->h_pos.data(), sizeof(int32_t) * n_frames, cudaMemcpyHostToDevice, st));
+    }
+    int* d_pos = n->d_pos;
     double *d_v = nullptr, *d_states = nullptr, *d_zi = nullptr;
     std::vector<double> zi_host((size_t)n_sessions * ord, 0.0);
     if (lp_state) memcpy(zi_host.data(), lp_state, sizeof(double) * n_sessions * ord);
@@ -163,12 +179,12 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
     cudaError_t e = cudaSuccess;
     if (rc == SGS_OK) {
         if (!d_blocks) { e = cudaMallocAsync((void**)&d_blocks, sizeof(double) * (size_t)n_sessions * n_frames * kBlk, st); own_blocks = true; }
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_pos, sizeof(int) * n_frames, st);
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_v, sizeof(double) * (size_t)n_sessions * n_out, st);
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_states, sizeof(double) * 2 * (size_t)n_sessions * n_chunks * kLpMaxOrd, st);
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_zi, sizeof(double) * (size_t)n_sessions * ord, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pos, positions, sizeof(int) * n_frames, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi_host.data(), sizeof(double) * n_sessions * ord, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = lp_state ? cudaMemcpyAsync(d_zi, zi_host.data(), sizeof(double) * n_sessions * ord, cudaMemcpyHostToDevice, st)
+                         : cudaMemsetAsync(d_zi, 0, sizeof(double) * n_sessions * ord, st);
         if (e != cudaSuccess) rc = cuda_fail(e, "scratch", __FILE__, __LINE__);
     }
     if (rc == SGS_OK) {
@@ -190,7 +206,6 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
     }
     const bool sync = s_pcm.host || s_flt.host || s_blk.host;
     if (own_blocks && d_blocks) cudaFreeAsync(d_blocks, st);
-    if (d_pos) cudaFreeAsync(d_pos, st);
     if (d_v) cudaFreeAsync(d_v, st);
     if (d_states) cudaFreeAsync(d_states, st);
     if (d_zi) cudaFreeAsync(d_zi, st);
