@@ -9,7 +9,7 @@
 namespace sgs {
 constexpr int kFft = 256, kHalf = 128, kHop = 160, kBlk = 480, kBins = 129;
 constexpr int kLpMaxOrd = 8;
-struct GlNodeTables { const double* window; const cplx* tw_half; const cplx* tw_full; const int* inv_idx; const double* inv_w; };
+struct GlNodeTables { const double* window; const cplx* tw_full; const cplx* tw_t; const int* inv_idx; const double* inv_w; };
 struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
 int gl_blocks_run(const double* logmel, const double* noise, unsigned long long seed, double* blocks, const GlNodeTables& tab,
                   int n_sessions, int n_frames, int n_mels, int first_frame, int iters, long long ring_base, int ring_len,
@@ -26,6 +26,7 @@ int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, 
 struct GlBatchTables { const double* window; const cplx* tw_half; const cplx* tw_full; const int* inv_idx; const double* inv_w; };
 int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int n_utt, int T, int n_mels, int iters,
                  long long x_len, double* mx, short* pcm, cudaStream_t st);
+int exp_angle_run(const double* im, const double* re, long long n, double* out, cudaStream_t st);
 int logmel_run(const double* audio, long long n_audio, const double* window, const cplx* tw_half, const cplx* tw_full,
                const double* mel, int n_mels, long long n_frames, int shift, int pad, double* out, cudaStream_t st);
 }  // namespace sgs
@@ -55,7 +56,7 @@ struct sgs_gl_node {
     double norm_div = 1.01;
     sgs::LpCoefs lp;
     double *d_window = nullptr, *d_ola = nullptr, *d_inv_w = nullptr, *d_phi = nullptr, *d_phi_sub = nullptr;
-    sgs::cplx *d_tw_half = nullptr, *d_tw_full = nullptr;
+    sgs::cplx *d_tw_full = nullptr, *d_tw_t = nullptr;
     int* d_inv_idx = nullptr;
     int lp_chunk = 0;
     // streaming state (sgs_gl_node_push): previous spectral frame + new ones, block ring, low-pass state
@@ -82,7 +83,7 @@ extern "C" {
 void sgs_gl_node_destroy(sgs_gl_node* n) {
     if (!n) return;
     cudaFree(n->d_window); cudaFree(n->d_ola); cudaFree(n->d_inv_w); cudaFree(n->d_phi); cudaFree(n->d_phi_sub);
-    cudaFree(n->d_tw_half); cudaFree(n->d_tw_full); cudaFree(n->d_inv_idx);
+    cudaFree(n->d_tw_full); cudaFree(n->d_tw_t); cudaFree(n->d_inv_idx);
     cudaFree(n->d_mel); cudaFree(n->d_ring); cudaFree(n->d_lp); cudaFree(n->d_noise); cudaFree(n->d_pcm); cudaFree(n->d_pos);
     delete n;
 }
@@ -109,18 +110,28 @@ int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len,
     for (int i = 0; i <= lp_order; ++i) { n->lp.b[i] = lp_b[i]; n->lp.a[i] = lp_a[i]; }
     for (int i = 0; i < kBins * 2; ++i)
         if (inv_idx[i] < 0 || inv_idx[i] >= n_mels) { delete n; set_error("inverse-mel tap index out of range"); return SGS_ERR_ARG; }
-    std::vector<cplx> th(kHalf), tf(kBins);
+    std::vector<cplx> tf(kBins);
     const double pi = 3.14159265358979323846;
-    for (int t = 0; t < kHalf; ++t) th[t] = cplx{cos(2.0 * pi * t / kHalf), -sin(2.0 * pi * t / kHalf)};
     for (int k = 0; k < kBins; ++k) tf[k] = cplx{cos(2.0 * pi * k / kFft), -sin(2.0 * pi * k / kFft)};
     // exact values at the quadrant points keep the DC / Nyquist algebra free of 1e-17 leakage
-    th[0] = cplx{1, 0}; th[kHalf / 4] = cplx{0, -1}; th[kHalf / 2] = cplx{-1, 0}; th[3 * kHalf / 4] = cplx{0, 1};
     tf[0] = cplx{1, 0}; tf[kFft / 4] = cplx{0, -1}; tf[kFft / 2] = cplx{-1, 0};
+    // W128^(l k1) for the register-FFT kernel (gl_blocks8.cuh): [k1][l] with rows padded to 9 entries
+    std::vector<cplx> tt(16 * 9, cplx{0, 0});
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int l = 0; l < 8; ++l) {
+            const int ex = (l * k1) % kHalf;
+            cplx w{cos(2.0 * pi * ex / kHalf), -sin(2.0 * pi * ex / kHalf)};
+            if (ex == 0) w = cplx{1, 0};
+            else if (ex == kHalf / 4) w = cplx{0, -1};
+            else if (ex == kHalf / 2) w = cplx{-1, 0};
+            else if (ex == 3 * kHalf / 4) w = cplx{0, 1};
+            tt[k1 * 9 + l] = w;
+        }
     cudaError_t e = upload((void**)&n->d_window, window, sizeof(double) * kFft);
+    if (e == cudaSuccess) e = upload((void**)&n->d_tw_t, tt.data(), sizeof(cplx) * tt.size());
     if (e == cudaSuccess) e = upload((void**)&n->d_ola, ola_window, sizeof(double) * kBlk);
     if (e == cudaSuccess) e = upload((void**)&n->d_inv_idx, inv_idx, sizeof(int) * kBins * 2);
     if (e == cudaSuccess) e = upload((void**)&n->d_inv_w, inv_w, sizeof(double) * kBins * 2);
-    if (e == cudaSuccess) e = upload((void**)&n->d_tw_half, th.data(), sizeof(cplx) * kHalf);
     if (e == cudaSuccess) e = upload((void**)&n->d_tw_full, tf.data(), sizeof(cplx) * kBins);
     if (e == cudaSuccess) e = upload((void**)&n->d_phi, lp_phi, sizeof(double) * lp_order * lp_order);
     if (e == cudaSuccess) e = upload((void**)&n->d_phi_sub, lp_phi_sub, sizeof(double) * lp_order * lp_order);
@@ -188,7 +199,7 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
         if (e != cudaSuccess) rc = cuda_fail(e, "scratch", __FILE__, __LINE__);
     }
     if (rc == SGS_OK) {
-        GlNodeTables tab{n->d_window, n->d_tw_half, n->d_tw_full, n->d_inv_idx, n->d_inv_w};
+        GlNodeTables tab{n->d_window, n->d_tw_full, n->d_tw_t, n->d_inv_idx, n->d_inv_w};
         rc = gl_blocks_run((const double*)s_mel.dev, (const double*)s_noise.dev, seed, d_blocks, tab, n_sessions, n_frames,
                            n->n_mels, first, n->iterations, 0, 0, st);
     }
@@ -354,7 +365,7 @@ int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* 
     for (int i = 0; i < kBlockRing; ++i) { fr.ring_pos[i] = s->ring_pos[i]; fr.ring_index[i] = s->ring_index[i]; }
     int rc = SGS_OK;
     if (fr.n > 0) {
-        GlNodeTables tab{s->d_window, s->d_tw_half, s->d_tw_full, s->d_inv_idx, s->d_inv_w};
+        GlNodeTables tab{s->d_window, s->d_tw_full, s->d_tw_t, s->d_inv_idx, s->d_inv_w};
         // local frame j (row j of d_mel) is running frame k0 - 1 + j; blocks for local frames [1 + skip, n]
         rc = gl_blocks_run(s->d_mel, noise ? s->d_noise : nullptr, seed, s->d_ring, tab, 1, n + 1, nm, 1 + skip, s->iterations,
                            k0 - 1, kBlockRing, st);
@@ -380,6 +391,23 @@ int sgs_gl_node_push(sgs_gl_node* s, const double* logmel, int n, const int32_t*
     int rc = gl_node_enqueue(s, logmel, n, pos, pos_before, noise, seed, nullptr, n_pcm, st);
     if (rc == SGS_OK && *n_pcm > 0) SGS_CUDA(cudaMemcpyAsync(pcm, s->d_pcm, sizeof(short) * *n_pcm, cudaMemcpyDeviceToHost, st));
     if (rc == SGS_OK) SGS_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+/* Test hook: out[i] = exp(angle(re[i] + 1j*im[i])) as k_gl_blocks evaluates it (GriffinLim.py:93). */
+int sgs_exp_angle(const double* im, const double* re, int64_t n, double* out, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(im && re && out && n >= 0, "bad arguments");
+    Staged si, sr, so;
+    int rc = stage_in(si, im, sizeof(double) * (size_t)n, st);
+    if (rc == SGS_OK) rc = stage_in(sr, re, sizeof(double) * (size_t)n, st);
+    if (rc == SGS_OK) rc = stage_out(so, out, sizeof(double) * (size_t)n, st);
+    if (rc == SGS_OK) rc = exp_angle_run((const double*)si.dev, (const double*)sr.dev, n, (double*)so.dev, st);
+    if (rc == SGS_OK) rc = finish_out(so, st);
+    const bool sync = so.host != nullptr;
+    release(si, st); release(sr, st); release(so, st);
+    if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
     return rc;
 }
 

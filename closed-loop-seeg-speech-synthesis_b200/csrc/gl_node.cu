@@ -11,32 +11,30 @@
 //     division skipped where the window sum is exactly 0.
 //   * order-5 low-pass (scipy.signal.lfilter, state carried across hops), clip, int16 truncation (GriffinLim.py:169-174).
 //
-// k_gl_blocks: one warp per block; waveform, FFT work buffers and spectra live in shared memory / registers; FP64
-//              throughout (the branch cut of angle() makes the iteration chaotic under fp32 round-off).
+// k_gl_blocks8 (gl_blocks8.cuh): 8 lanes per STFT frame, FFTs in registers, one shared-memory transposition per
+//              transform, exp(angle) as polynomial pieces (exp_angle.cuh); FP64 throughout (the branch cut of angle()
+//              makes the iteration chaotic under fp32 round-off).
 // k_gl_ola:    gathers the <= 4 blocks covering each output sample in arrival order.
 // k_lp_*:      the IIR low-pass as an exact chunked scan over the 5-state recurrence (zero-state chunk pass,
 //              sequential 5x5 carry, final pass with clip + int16).
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "fft.cuh"
+#include "exp_angle.cuh"
 
 namespace sgs {
 
 constexpr int kFft = 256, kHalf = 128, kHop = 160, kBlk = 480, kBins = 129;
-constexpr int kGlWarps = 4;
 
 struct GlNodeTables {               // device pointers, built once per node configuration
     const double* window;           // blackman(256)
-    const cplx* tw_half;            // exp(-2 pi i t / 128), t < 128
     const cplx* tw_full;            // exp(-2 pi i k / 256), k <= 128
+    const cplx* tw_t;               // [16][9] W128^(l k1) (register-FFT kernel, gl_blocks8.cuh)
     const int* inv_idx;             // [129][2] mel index of each inverse-mel tap
     const double* inv_w;            // [129][2] weight (0 where unused)
 };
 
-struct GlWarpSmem {
-    double x[kBlk];
-    cplx a[2][kHalf];               // one work buffer per STFT frame of the block (stages are read-sync-write-sync)
-};
 
 __device__ __forceinline__ double uniform01(unsigned long long seed, unsigned long long item, unsigned idx) {
     // counter-based generator for throughput runs (parity runs pass the reference's MT19937 draws explicitly)
@@ -56,173 +54,23 @@ __device__ __noinline__ double mel_magnitude(const double* lm, const int* inv_id
     return isfinite(v) ? v : 0.0;                                           // MelFilterBank.makeNormal
 }
 
-// exp(np.angle(re + 1j*im)): kept out of line, it is the bulk of the code and is called 8 times per iteration
-__device__ __noinline__ double exp_angle(double im, double re) { return exp(atan2(im, re)); }
-
-// One Stockham stage of the 128-point transform applied to BOTH work buffers at once (two independent transforms
-// in flight per warp hide the shared-memory latency).  Every lane reads all its inputs, the warp syncs, then
-// writes: a single buffer per transform is enough.
-template <int R, int NS, int SIGN>
-__device__ __forceinline__ void stage2(cplx* __restrict__ a0, cplx* __restrict__ a1, const cplx* __restrict__ tw, int lane) {
-    constexpr int M = kHalf / R, PER = M / 32;
-    cplx v[2][PER][R];
-#pragma unroll
-    for (int p = 0; p < PER; ++p) {
-        const int j = lane + 32 * p;
-#pragma unroll
-        for (int r = 0; r < R; ++r) { v[0][p][r] = a0[j + r * M]; v[1][p][r] = a1[j + r * M]; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int p = 0; p < PER; ++p) {
-        const int j = lane + 32 * p;
-        const int k = j % NS;
-        if (NS > 1) {
-#pragma unroll
-            for (int r = 1; r < R; ++r) {
-                cplx w = tw[r * k * (kHalf / (NS * R))];
-                if (SIGN > 0) w.y = -w.y;
-                v[0][p][r] = cmul(v[0][p][r], w);
-                v[1][p][r] = cmul(v[1][p][r], w);
-            }
-        }
-        Butterfly<R, SIGN>::run(v[0][p]);
-        Butterfly<R, SIGN>::run(v[1][p]);
-        const int j0 = (j / NS) * NS * R + k;
-#pragma unroll
-        for (int q = 0; q < R; ++q) { a0[j0 + q * NS] = v[0][p][q]; a1[j0 + q * NS] = v[1][p][q]; }
-    }
-    __syncwarp();
+// out-of-line copy of the pair evaluation: one body in the instruction cache, called 4 times per iteration
+__device__ __noinline__ double2 exp_angle_pair_call(double im1, double re1, double im2, double re2) {
+    double a, b;
+    exp_angle_pair(im1, re1, im2, re2, a, b);
+    return make_double2(a, b);
 }
 
-// Forward transform only, out of line (one copy of the four stages in the instruction cache): the inverse is taken
-// as conj(FFT(conj(Z))), with the conjugations folded into the split before it and the unpack after it.
-__device__ __noinline__ void fft128x2(cplx* a0, cplx* a1, const cplx* tw, int lane) {
-    stage2<4, 1, -1>(a0, a1, tw, lane);
-    stage2<4, 4, -1>(a0, a1, tw, lane);
-    stage2<4, 16, -1>(a0, a1, tw, lane);
-    stage2<2, 64, -1>(a0, a1, tw, lane);
+// exp(np.angle(re + 1j*im)) for one value (block set-up only; the iteration uses exp_angle_pair, exp_angle.cuh)
+__device__ __forceinline__ double exp_angle(double im, double re) {
+    double a, b;
+    exp_angle_pair(im, re, im, re, a, b);
+    return a;
 }
 
-__global__ void __launch_bounds__(kGlWarps * 32)
-k_gl_blocks(const double* __restrict__ logmel, const double* __restrict__ noise, unsigned long long seed,
-            double* __restrict__ blocks, const GlNodeTables tab, int n_frames, int n_mels, int first_frame, int iters,
-            long long n_items, long long ring_base, int ring_len) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_window = reinterpret_cast<double*>(smem_raw);                 // [256]
-    cplx* s_tw_half = reinterpret_cast<cplx*>(s_window + kFft);             // [128]
-    cplx* s_tw_full = s_tw_half + kHalf;                                    // [129] (+1 pad)
-    GlWarpSmem* ws_all = reinterpret_cast<GlWarpSmem*>(s_tw_full + kBins + 1);
-    for (int i = threadIdx.x; i < kFft; i += blockDim.x) s_window[i] = tab.window[i];
-    for (int i = threadIdx.x; i < kHalf; i += blockDim.x) s_tw_half[i] = tab.tw_half[i];
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) s_tw_full[i] = tab.tw_full[i];
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    GlWarpSmem& ws = ws_all[warp];
-    const int per_sess = n_frames - first_frame;                            // blocks per session
-    const double exp_pi = exp_angle(0.0, -1.0);                             // exp(angle(negative real)) = e^pi
-    // bin pairs (k, 128-k) owned by this lane in the two rounds: k = lane (round 0; lane 0 takes the self-pair 64) and
-    // k = lane + 32 (round 1).  DC and Nyquist are purely real and handled by lane 0 without transcendentals.
-    const int kr0 = lane == 0 ? kHalf / 2 : lane, kr1 = lane + 32;
-
-    auto magnitude = [&](const double* lm, int bin) -> double { return mel_magnitude(lm, tab.inv_idx, tab.inv_w, bin); };
-
-    for (long long item = (long long)blockIdx.x * kGlWarps + warp; item < n_items; item += (long long)gridDim.x * kGlWarps) {
-        const int sess = (int)(item / per_sess);
-        const int k = first_frame + (int)(item - (long long)sess * per_sess);
-        const long long frame = (long long)sess * n_frames + k;
-
-        // magnitudes of the two spectral frames k-1, k at this lane's bins: [frame][round][k / 128-k], plus DC / Nyquist
-        double S[2][2][2], Sdc[2], Sny[2];
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            const double* lm = logmel + (frame - 1 + f) * n_mels;
-            S[f][0][0] = magnitude(lm, kr0); S[f][0][1] = magnitude(lm, kHalf - kr0);
-            S[f][1][0] = magnitude(lm, kr1); S[f][1][1] = magnitude(lm, kHalf - kr1);
-            Sdc[f] = magnitude(lm, 0); Sny[f] = magnitude(lm, kHalf);
-        }
-        for (int i = lane; i < kBlk; i += 32)
-            ws.x[i] = noise ? noise[frame * kBlk + i] : uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)i);
-        __syncwarp();
-
-#pragma unroll 1
-        for (int it = 0; it < iters; ++it) {
-            // ---- analysis: window + pack both frames (offsets 0 and 160), forward transforms -------------------
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int n = lane + 32 * i;
-                const double w0 = s_window[2 * n], w1 = s_window[2 * n + 1];
-                ws.a[0][n] = cplx{ws.x[2 * n] * w0, ws.x[2 * n + 1] * w1};
-                ws.a[1][n] = cplx{ws.x[kHop + 2 * n] * w0, ws.x[kHop + 2 * n + 1] * w1};
-            }
-            __syncwarp();
-            fft128x2(ws.a[0], ws.a[1], s_tw_half, lane);
-            // ---- per bin pair: real-FFT split, Z = S * exp(angle(X)) (real: the reference has no 1j, quirk Q1), and
-            //      the inverse split, written back in place ---------------------------------------------------
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-                cplx* a = ws.a[f];
-                const cplx a0 = a[0];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int kk = r == 0 ? kr0 : kr1, k2 = kHalf - kk;
-                    const cplx A = a[kk], B = a[k2], w = s_tw_full[kk], w2 = s_tw_full[k2];
-                    // X[kk] from (A, conj B), X[k2] from (B, conj A)
-                    const cplx d1 = cplx{A.x - B.x, A.y + B.y}, t1 = cmul(w, d1);
-                    const double re1 = 0.5 * (A.x + B.x) + 0.5 * t1.y, im1 = 0.5 * (A.y - B.y) - 0.5 * t1.x;
-                    const cplx d2 = cplx{B.x - A.x, B.y + A.y}, t2 = cmul(w2, d2);
-                    const double re2 = 0.5 * (B.x + A.x) + 0.5 * t2.y, im2 = 0.5 * (B.y - A.y) - 0.5 * t2.x;
-                    const double z1 = S[f][r][0] * exp_angle(im1, re1);
-                    const double z2 = S[f][r][1] * exp_angle(im2, re2);
-                    // inverse split of a real spectrum: Zin[k] = (z_k + z_{128-k}) + i e^{+i th_k} (z_k - z_{128-k})
-                    const double sm = z1 + z2, df = z1 - z2;
-                    // (stored conjugated: the inverse transform below is conj(FFT(conj(.))))
-                    a[kk] = cplx{fma(w.y, df, sm), -(w.x * df)};
-                    if (k2 != kk) a[k2] = cplx{fma(w2.y, -df, sm), w2.x * df};
-                }
-                if (lane == 0) {
-                    // DC and Nyquist are real with imag = +0.0 in numpy: angle is 0 or pi
-                    const double xdc = a0.x + a0.y, xny = a0.x - a0.y;
-                    const double zdc = Sdc[f] * ((xdc < 0.0 || (xdc == 0.0 && signbit(xdc))) ? exp_pi : 1.0);
-                    const double zny = Sny[f] * ((xny < 0.0 || (xny == 0.0 && signbit(xny))) ? exp_pi : 1.0);
-                    a[0] = cplx{zdc + zny, -(zdc - zny)};
-                }
-            }
-            __syncwarp();
-            fft128x2(ws.a[0], ws.a[1], s_tw_half, lane);
-            // ---- synthesis: x = irfft(Z0) w at 0  (+)  irfft(Z1) w at 160; nothing reaches [416, 480) ---------
-            constexpr double scale = 1.0 / kFft;
-            double r0[4][2], r1[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int n = lane + 32 * i;
-                const double w0 = s_window[2 * n], w1 = s_window[2 * n + 1];
-                r0[i][0] = (ws.a[0][n].x * scale) * w0; r0[i][1] = (-ws.a[0][n].y * scale) * w1;
-                r1[i][0] = (ws.a[1][n].x * scale) * w0; r1[i][1] = (-ws.a[1][n].y * scale) * w1;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {                               // frame 0 first: the overlap is (0 + r0) + r1
-                const int n = lane + 32 * i;
-                ws.x[2 * n] = r0[i][0];
-                ws.x[2 * n + 1] = r0[i][1];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = 2 * (lane + 32 * i);
-                ws.x[kHop + m] = (m < kFft - kHop) ? ws.x[kHop + m] + r1[i][0] : r1[i][0];
-                ws.x[kHop + m + 1] = (m + 1 < kFft - kHop) ? ws.x[kHop + m + 1] + r1[i][1] : r1[i][1];
-            }
-            for (int i = kHop + kFft + lane; i < kBlk; i += 32) ws.x[i] = 0.0;
-            __syncwarp();
-        }
-        // batch: one row per (session, frame); streaming: slot of the running frame number in a power-of-two ring
-        const long long row = ring_len ? ((ring_base + k) & (ring_len - 1)) : frame;
-        for (int i = lane; i < kBlk; i += 32) blocks[row * kBlk + i] = ws.x[i];
-        __syncwarp();
-    }
-}
+}  // namespace sgs
+#include "gl_blocks8.cuh"
+namespace sgs {
 
 // ------------------------------------------------------------------------------------------------
 // overlap-add + window-sum normalisation, linear-time restatement of the node's ring buffers.
@@ -371,6 +219,20 @@ __global__ void k_lp_carry(const double* __restrict__ e, double* __restrict__ st
     for (int i = 0; i < ORD; ++i) zi[sess * ORD + i] = s[i];
 }
 
+// test hook: the kernel's exp(angle()) on arbitrary inputs (tests/test_gpu_decode.py checks it against numpy and mpmath)
+__global__ void k_exp_angle(const double* __restrict__ im, const double* __restrict__ re, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = exp_angle(im[i], re[i]);
+}
+
+int exp_angle_run(const double* im, const double* re, long long n, double* out, cudaStream_t st) {
+    if (n <= 0) return SGS_OK;
+    k_exp_angle<<<ceil_div(n, 256), 256, 0, st>>>(im, re, n, out);
+    SGS_LAUNCHED();
+    SGS_CUDA(cudaGetLastError());
+    return SGS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
@@ -379,12 +241,17 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
                   cudaStream_t st) {
     const long long n_items = (long long)n_sessions * (n_frames - first_frame);
     if (n_items <= 0) return SGS_OK;
-    const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kHalf + kBins + 1) + sizeof(GlWarpSmem) * kGlWarps;
+    ProfScope ps(kProfGlBlocks, st);
+    // 8 warps x 2 CTAs per SM: 128 registers per thread and 113 KB of shared memory per CTA (16 resident warps = 32 blocks)
+    constexpr int W = 8;
+    const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kG8SLen + kG8BufCplx) + sizeof(G8WarpSmem) * W;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_gl_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    long long want = (n_items + kGlWarps - 1) / kGlWarps;
-    const int grid = (int)(want < 148 * 5 * 8 ? want : 148 * 5 * 8);
-    { ProfScope ps(kProfGlBlocks, st); k_gl_blocks<<<grid, kGlWarps * 32, smem, st>>>(logmel, noise, seed, blocks, tab, n_frames, n_mels, first_frame, iters, n_items, ring_base, ring_len); }
+    if (!attr) { cudaFuncSetAttribute(k_gl_blocks8<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    const long long n_pairs = (n_items + 1) / 2, want = (n_pairs + W - 1) / W;
+    const int grid = (int)(want < 148LL * 2 * 8 ? want : 148LL * 2 * 8);
+    const G8Tables t8{tab.window, tab.tw_t, tab.tw_full, tab.inv_idx, tab.inv_w};
+    k_gl_blocks8<W, 2><<<grid, W * 32, smem, st>>>(logmel, noise, seed, blocks, t8, n_frames, n_mels, first_frame, iters, n_items,
+                                                   ring_base, ring_len);
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;

@@ -193,6 +193,10 @@ int sgs_gl_batch_synthesize(sgs_gl_batch* plan, const double* logmel, int n_utt,
 int sgs_logmel(const double* audio, int64_t n_audio, const double* window, int win_len, int shift, const double* mel,
                int n_bins, int n_mels, int64_t n_frames, double* out, void* stream);
 
+/* Test hook: out[i] = exp(np.angle(re[i] + 1j*im[i])), the per-bin operation of the node's phase step (GriffinLim.py:93)
+ * exactly as k_gl_blocks evaluates it (csrc/exp_angle.cuh). */
+int sgs_exp_angle(const double* im, const double* re, int64_t n, double* out, void* stream);
+
 /* Dequantization node alone (livenodes/Dequantization.py:15-18; local/quantization.py:125-135 with smooth = 0):
  * out[r][b] = medians[b][labels[r][b]], optionally smoothed across bins with taps[2*radius+1] ('reflect'). */
 int sgs_dequantize(const double* medians, int n_bins, int n_levels, const double* taps, int radius,
