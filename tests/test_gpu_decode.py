@@ -226,3 +226,37 @@ def test_exp_angle_matches_numpy_and_mpmath():
         t = mp.exp(mp.atan2(mp.mpf(float(im[i])), mp.mpf(float(re[i]))))
         worst = max(worst, float(abs(mp.mpf(float(out[i])) - t) / t))
     assert worst < 3 * 2.2e-16, worst
+
+
+def test_config1_full_size_decode_matches_oracle():
+    """BASELINE config 1 at full size - 64 ch @ 1024 Hz, 5 minutes (307 200 samples, 30 000 frames) - decoded on the device
+    and by the CPU oracle from the same synthetic recording, random-weight model of the trained architecture and the
+    same np.random.rand start of every Griffin-Lim block: features to 1e-9, class indices and spectrogram bit-exact,
+    int16 audio within 1 LSB."""
+    import decode
+    from sgs.synth import default_medians
+    sr, n_ch, seconds = 1024, 64, 300.0
+    rng = np.random.default_rng(11)
+    W = rng.normal(0, 0.3, (40, 9, 150))
+    b = rng.normal(0, 1.0, (40, 9))
+    cls = np.tile(np.arange(9, dtype=np.float64), (40, 1))
+    select = rng.permutation(5 * n_ch)[:150].astype(np.int32)
+    medians = default_medians(40, 9)
+    x = synth.seeg_session(21, n_ch, sr, seconds)                              # float32 (T x C)
+    feats = O.ecog_feat_calc(x.astype(np.float64), sr, 50, 10, 4, 5, 50, 32)
+    assert feats.shape == (30000, 5 * n_ch)
+    want_labels, _ = O.lda_predict_packed(feats, W, b, cls, select)
+    want_spec = O.dequantization_node(want_labels, medians)
+    noise = np.random.RandomState(4100).rand(len(want_spec), 480)
+    want_pcm, _ = O.GriffinLimNode(16, 10, 16000, 40, 8, norm_factor=10).synthesize(want_spec, noise)
+
+    dec = decode.OfflineDecoder((W, b, cls), medians, select, sr, gl_norm=10, packet_size=32)
+    lp = dec.features.log_power(x, online=True, chunk_size=32)
+    assert np.abs(dec.features.stack(lp, online=True) - feats).max() < 1e-9
+    labels, spec = dec.lda.decode(lp, order=4, step=5, first_row=0, smooth=True)     # 30 000 frames: the tensor-core path
+    assert np.array_equal(labels, want_labels)
+    assert np.array_equal(spec, want_spec)
+    pcm = dec.gl.synthesize(spec, noise)
+    assert pcm.shape == want_pcm.shape == (4799840,)
+    d = np.abs(pcm.astype(int) - want_pcm.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3
