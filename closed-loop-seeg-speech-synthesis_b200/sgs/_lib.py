@@ -72,6 +72,7 @@ def _declare(lib):
     fn('sgs_lda_stats', c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
        c_void_p, c_void_p, c_void_p, c_void_p)
     fn('sgs_exp_angle', c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p)
+    fn('sgs_decimate', c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p)
     fn('sgs_dequantize', c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p)
     return lib
 

@@ -6,8 +6,8 @@
 Feature extraction, the log-mel target, quantisation, Spearman ranking and the LDA statistics run on the device;
 the 40 small eigen-problems are solved on the host and wrapped into scikit-learn LinearDiscriminantAnalysis
 objects (when scikit-learn is importable) so the pickled model is interchangeable with the reference's.
-The 48 kHz -> 16 kHz decimation of the audio (train.py:125) is audio-side preparation and stays scipy's
-(SURVEY.md 8f rank 1); pass sfreq_audio=16000 to skip it."""
+The 48 kHz -> 16 kHz decimation of the audio (train.py:125, scipy.signal.decimate) runs on the device too
+(sgs.spectrogram.decimate)."""
 import logging
 import os
 import pickle
@@ -55,7 +55,7 @@ def train_estimators(estimators, x_train, y_train):
 def compute_features(eeg, sfreq_eeg, audio, audio_sr):
     x_train = herff2016_b(eeg, sfreq_eeg, 0.05, 0.01)
     if audio_sr != 16000:
-        from scipy.signal import decimate
+        from sgs.spectrogram import decimate
         audio = decimate(audio, int(round(audio_sr / 16000)))
     y_train = compute_spectrogram(audio, 16000, 0.016, 0.01)
     return x_train, y_train

@@ -197,6 +197,13 @@ int sgs_logmel(const double* audio, int64_t n_audio, const double* window, int w
  * exactly as k_gl_blocks evaluates it (csrc/exp_angle.cuh). */
 int sgs_exp_angle(const double* im, const double* re, int64_t n, double* out, void* stream);
 
+/* scipy.signal.decimate(audio, q) as train.py:125 uses it (ftype='iir', zero_phase=True): out[j] = sosfiltfilt(sos, audio)[q*j],
+ * j < ceil(n/q).  sos[n_sections][6] = cheby1(8, 0.05, 0.8/q, 'sos'), zi[n_sections][2] = sosfilt_zi(sos),
+ * edge = 3*(2*n_sections+1) (sosfiltfilt's odd-extension length), warm = samples after which the filter state has
+ * forgotten its start to 2^-70 (host: from the largest pole radius).  Both passes run as chunked scans over time. */
+int sgs_decimate(const double* audio, int64_t n, int q, const double* sos, const double* zi, int n_sections, int edge, int warm,
+                 double* out, void* stream);
+
 /* Dequantization node alone (livenodes/Dequantization.py:15-18; local/quantization.py:125-135 with smooth = 0):
  * out[r][b] = medians[b][labels[r][b]], optionally smoothed across bins with taps[2*radius+1] ('reflect'). */
 int sgs_dequantize(const double* medians, int n_bins, int n_levels, const double* taps, int radius,

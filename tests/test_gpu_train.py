@@ -133,3 +133,17 @@ def test_lda_stats_tensor_core_is_exact(n, nf, nb, monkeypatch):
     # bit-reproducible run to run (integer atomics commute)
     again = training.lda_stats(X, sel, lab)
     assert np.array_equal(again['G'], tc['G']) and np.array_equal(again['sums'], tc['sums'])
+
+
+@pytest.mark.parametrize('q,n', [(3, 48000 * 7 + 1), (3, 100), (2, 30000), (4, 12345)])
+def test_decimate_matches_scipy(q, n):
+    """sgs.spectrogram.decimate == scipy.signal.decimate(x, q) (cheby1 order 8, sosfiltfilt, every q-th sample) although
+    both passes run as chunked scans with truncated warm-up: agreement to fp64 round-off, edges included."""
+    from scipy.signal import decimate as sp_decimate
+    from sgs.spectrogram import decimate
+    x = synth.audio_session(3, n / 48000.0 + 0.01, 48000)[:n].astype(np.float64)
+    x += 0.3                                                  # a DC offset exercises the steady-state initial conditions
+    want = sp_decimate(x, q)
+    got = decimate(x, q)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
