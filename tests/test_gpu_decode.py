@@ -260,3 +260,40 @@ def test_config1_full_size_decode_matches_oracle():
     assert pcm.shape == want_pcm.shape == (4799840,)
     d = np.abs(pcm.astype(int) - want_pcm.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 2e-3
+
+
+def test_config5_full_length_sessions_causality_and_independence():
+    """BASELINE config 5 session shape at full length (128 ch x 600 s @ 2048 Hz): properties that do not need a 10-minute CPU run.
+    (1) causality: every stage is causal, so the first frames of the full decode equal the CPU oracle's decode of the first
+        seconds alone; (2) independence: a session decodes to the same bits alone or inside a batch."""
+    import decode
+    import torch
+    from sgs.synth import default_medians
+    sr, n_ch, seconds, head = 2048, 128, 600.0, 8.0
+    rng = np.random.default_rng(13)
+    W = rng.normal(0, 0.3, (40, 9, 150)); b = rng.normal(0, 1.0, (40, 9))
+    cls = np.tile(np.arange(9, dtype=np.float64), (40, 1))
+    select = rng.permutation(5 * n_ch)[:150].astype(np.int32)
+    medians = default_medians(40, 9)
+    xs = np.stack([synth.seeg_session(40 + s, n_ch, sr, seconds) for s in range(2)])           # (2, 1 228 800, 128) float32
+    dec = decode.OfflineDecoder((W, b, cls), medians, select, sr, gl_norm=10, packet_size=64)
+    xd = torch.from_numpy(xs).cuda()
+    spec2, audio2 = dec.decode(xd, None, seed=3)
+    spec2, audio2 = spec2.cpu().numpy(), audio2.cpu().numpy()
+    assert spec2.shape == (2, 60000, 40) and audio2.shape == (2, 9599840)
+    for s in range(2):
+        spec1, audio1 = dec.decode(xd[s:s + 1], None, seed=3)
+        assert np.array_equal(spec1[0].cpu().numpy(), spec2[s])
+    # audio with the device noise generator depends on (seed, session index): session 0 alone == session 0 in the batch
+    spec1, audio1 = dec.decode(xd[0:1], None, seed=3)
+    assert np.array_equal(audio1[0].cpu().numpy(), audio2[0])
+    # causality against the oracle on the first `head` seconds of session 1
+    n_head = int(head * sr)
+    feats = O.ecog_feat_calc(xs[1, :n_head].astype(np.float64), sr, 50, 10, 4, 5, 50, 64)
+    want_labels, _ = O.lda_predict_packed(feats, W, b, cls, select)
+    want_spec = O.dequantization_node(want_labels, medians)
+    n = len(want_spec)
+    assert n >= 790
+    assert np.array_equal(spec2[1, :n], want_spec)
+    lp = dec.features.log_power(xd[1], online=True, chunk_size=64)
+    assert np.abs(dec.features.stack(lp, online=True)[:n].cpu().numpy() - feats).max() < 1e-9

@@ -200,3 +200,50 @@ def test_fused_chain_not_used_for_other_wirings(model):
     for i in range(0, len(x), 32):
         src.output_data(np.array(x[i:i + 32]))
     assert feat._chain is None and len(out) > 30
+
+
+def test_config2_streaming_chain_matches_oracle():
+    """BASELINE config 2 shape: 128 ch @ 2048 Hz pushed in 64-sample float32 packets through the decode.setup_decoder graph
+    (fused chain) == the CPU oracle's closed form of the reference chain on the same recording, model and noise draws."""
+    import decode
+    import oracle as O
+    from livenodes import Node
+    from sgs.synth import default_medians
+    sr, n_ch, seconds = 2048, 128, 6.0
+    rng = np.random.default_rng(12)
+    W = rng.normal(0, 0.3, (40, 9, 150)); b = rng.normal(0, 1.0, (40, 9))
+    cls = np.tile(np.arange(9, dtype=np.float64), (40, 1))
+    select = rng.permutation(5 * n_ch)[:150].astype(np.int32)
+    medians = default_medians(40, 9)
+
+    from sgs.training import PackedLDA
+    ests = []
+    for i in range(40):
+        e = PackedLDA()
+        e.coef_, e.intercept_, e.classes_ = W[i], b[i], cls[i]
+        ests.append(e)
+    blob = pickle.dumps(ests)
+    x = synth.seeg_session(31, n_ch, sr, seconds)
+    src = Node.Node(name='src', has_inputs=False)
+    rec_seeg, rec_spec, rec_audio = decode.setup_decoder(src, sr, blob, medians, [], select, gl_norm=10, packet_size=64,
+                                                         include_soundcard=False)
+    feat_node = src.output_classes[0].output_classes[0]
+    rows = []
+    feat_node.add_output(lambda f: rows.append(np.array(f, copy=True)))
+    np.random.seed(4200)
+    for i in range(0, len(x), 64):
+        src.output_data(np.array(x[i:i + 64]))
+    assert feat_node._chain is not None
+    spec = np.array(rec_spec.get_data())
+    audio = np.hstack(rec_audio.get_data())
+    n_frames = len(spec)
+    noise = np.zeros((n_frames, 480))
+    rs = np.random.RandomState(4200)
+    for k in range(1, n_frames):
+        noise[k] = rs.rand(480)
+    wx, wl, ws, wp, _ = O.decode_streaming(x.astype(np.float64), sr, pickle.loads(blob), select, medians, noise, gl_norm=10, chunk_size=64)
+    assert n_frames == len(ws) and n_frames > 590
+    assert np.abs(np.array(rows) - wx).max() < 1e-9
+    assert np.array_equal(spec, ws)
+    d = np.abs(audio.astype(int) - wp.astype(int))
+    assert audio.shape == wp.shape and d.max() <= 1 and (d > 0).mean() < 2e-3
