@@ -21,7 +21,7 @@ int gl_emit_stream_run(const double* block_ring, const double* ola_window, doubl
 int dequantize_run(const double* labels, const double* medians, const double* taps, int radius, int smooth, int n_bins,
                    int n_levels, long long n_rows, double* out, cudaStream_t st);
 int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, double* v, double* states, double* zi,
-                const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered,
+                double* zi_out, int carry_depth, const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered,
                 int n_sessions, int n_frames, int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st);
 struct GlBatchTables { const double* window; const cplx* tw_half; const cplx* tw_full; const int* inv_idx; const double* inv_w; };
 int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int n_utt, int T, int n_mels, int iters,
@@ -59,6 +59,7 @@ struct sgs_gl_node {
     sgs::cplx *d_tw_full = nullptr, *d_tw_t = nullptr;
     int* d_inv_idx = nullptr;
     int lp_chunk = 0;
+    int lp_carry_depth = 0;        // chunks after which Phi^depth is below 2^-70 (0: Phi is not small, sequential carry)
     // streaming state (sgs_gl_node_push): previous spectral frame + new ones, block ring, low-pass state
     double *d_mel = nullptr, *d_ring = nullptr, *d_lp = nullptr, *d_noise = nullptr;
     short* d_pcm = nullptr;
@@ -105,6 +106,16 @@ int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len,
     sgs_gl_node* n = new sgs_gl_node();
     n->n_mels = n_mels; n->iterations = iterations; n->norm_div = norm_div; n->lp_chunk = lp_chunk;
     n->first_frame = block_len - context_width - 1;
+    {
+        // |Phi|_inf^depth < 2^-70 bounds what the parallel carry drops (gl_node.cu:k_lp_carry_par)
+        double norm = 0.0;
+        for (int i = 0; i < lp_order; ++i) {
+            double row = 0.0;
+            for (int k = 0; k < lp_order; ++k) row += fabs(lp_phi[i * lp_order + k]);
+            norm = std::max(norm, row);
+        }
+        n->lp_carry_depth = (norm > 0.0 && norm < 0.25) ? (int)ceil(-70.0 * log(2.0) / log(norm)) : (norm == 0.0 ? 1 : 0);
+    }
     memset(&n->lp, 0, sizeof(n->lp));
     n->lp.ord = lp_order;
     for (int i = 0; i <= lp_order; ++i) { n->lp.b[i] = lp_b[i]; n->lp.a[i] = lp_a[i]; }
@@ -192,7 +203,7 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
         if (!d_blocks) { e = cudaMallocAsync((void**)&d_blocks, sizeof(double) * (size_t)n_sessions * n_frames * kBlk, st); own_blocks = true; }
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_v, sizeof(double) * (size_t)n_sessions * n_out, st);
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_states, sizeof(double) * 2 * (size_t)n_sessions * n_chunks * kLpMaxOrd, st);
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_zi, sizeof(double) * (size_t)n_sessions * ord, st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_zi, sizeof(double) * 2 * (size_t)n_sessions * ord, st);   // in, out
         if (e == cudaSuccess)
             e = lp_state ? cudaMemcpyAsync(d_zi, zi_host.data(), sizeof(double) * n_sessions * ord, cudaMemcpyHostToDevice, st)
                          : cudaMemsetAsync(d_zi, 0, sizeof(double) * n_sessions * ord, st);
@@ -204,13 +215,13 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
                            n->n_mels, first, n->iterations, 0, 0, st);
     }
     if (rc == SGS_OK)
-        rc = gl_emit_run(d_blocks, d_pos, n->d_ola, d_v, d_states, d_zi, n->d_phi, n->lp, n->norm_div, (short*)s_pcm.dev,
+        rc = gl_emit_run(d_blocks, d_pos, n->d_ola, d_v, d_states, d_zi, d_zi + (size_t)n_sessions * ord, n->lp_carry_depth, n->d_phi, n->lp, n->norm_div, (short*)s_pcm.dev,
                          (double*)s_flt.dev, n_sessions, n_frames, first, n_out, chunk, n_chunks, st);
     if (rc == SGS_OK) rc = finish_out(s_pcm, st);
     if (rc == SGS_OK && filtered) rc = finish_out(s_flt, st);
     if (rc == SGS_OK && blocks_out) rc = finish_out(s_blk, st);
     if (rc == SGS_OK && lp_state) {
-        e = cudaMemcpyAsync(zi_host.data(), d_zi, sizeof(double) * n_sessions * ord, cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(zi_host.data(), d_zi + (size_t)n_sessions * ord, sizeof(double) * n_sessions * ord, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = cuda_fail(e, "state readback", __FILE__, __LINE__);
         else memcpy(lp_state, zi_host.data(), sizeof(double) * n_sessions * ord);
