@@ -7,24 +7,11 @@
 // Here the same four device streams (their state is unchanged and shared with the single-node entry points) are
 // driven back to back on one CUDA stream; inputs and results go through page-locked staging owned by the chain.
 #include <algorithm>
-#include "common.cuh"
+#include "kernels.cuh"
 #include "../../include/sgs.h"
 
 namespace sgs {
 constexpr int kChainMaxFrames = 16, kChainMaxSamples = 128, kChainBlk = 480, kChainHopMax = 192;
-struct LdaGeom {
-    int n_bins, n_classes, n_features, n_levels;
-    int n_windows, n_channels, n_rows, first_row, order, step;
-    int smooth_radius;
-};
-int feat_stream_row_width(const sgs_feat_stream* s);
-int feat_stream_enqueue(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
-                        const int64_t* frame_index, int n_frames, double* d_rows, cudaStream_t st);
-int lda_rows_enqueue(const sgs_lda_model* m, const double* d_rows, int n_rows, int row_width, double* d_labels, double* d_spec,
-                     int smooth, cudaStream_t st);
-int lda_model_bins(const sgs_lda_model* m);
-int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
-                    uint64_t seed, short* d_pcm, int* n_pcm, cudaStream_t st);
 }  // namespace sgs
 
 struct sgs_chain {

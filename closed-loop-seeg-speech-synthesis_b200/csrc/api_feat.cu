@@ -1,16 +1,9 @@
 // C ABI for feature extraction (include/sgs.h).
 #include <math.h>
 #include <vector>
-#include "feat.cuh"
+#include "kernels.cuh"
 #include "../../include/sgs.h"
 
-namespace sgs {
-int feat_run(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* slots, const double* phi,
-             bool apply_phi, const long long* bounds, const int* kfirst, const int* starts, const double* zf,
-             const double* coef, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st);
-int stack_run(const double* feat, double* out, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,
-              int order, int step, cudaStream_t st);
-}  // namespace sgs
 
 struct sgs_feat_plan {
     int n_biquads = 0;
@@ -205,13 +198,6 @@ int sgs_feat_stack(const double* feat, int n_sessions, int n_windows, int n_chan
 // ---------------------------------------------------------------------------------------------------------------
 // streaming feature extraction (ECogFeatCalc node)
 // ---------------------------------------------------------------------------------------------------------------
-namespace sgs {
-constexpr int kSqRing = 256, kFeatRing = 32, kMaxFramesPerPush = 16;
-struct StreamFrames { int n; long long end[kMaxFramesPerPush]; long long index[kMaxFramesPerPush]; };
-int feat_stream_run(int n_biquads, const void* x, bool x_is_f64, int n, int n_channels, long long t0, double* z,
-                    double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int frame_size, int order, int step,
-                    double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st);
-}  // namespace sgs
 
 struct sgs_feat_stream {
     sgs_feat_plan* plan = nullptr;

@@ -2,34 +2,9 @@
 #include <math.h>
 #include <algorithm>
 #include <vector>
-#include "common.cuh"
-#include "fft.cuh"
+#include "kernels.cuh"
 #include "../../include/sgs.h"
 
-namespace sgs {
-constexpr int kFft = 256, kHalf = 128, kHop = 160, kBlk = 480, kBins = 129;
-constexpr int kLpMaxOrd = 8;
-struct GlNodeTables { const double* window; const cplx* tw_full; const cplx* tw_t; const int* inv_idx; const double* inv_w; };
-struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
-int gl_blocks_run(const double* logmel, const double* noise, unsigned long long seed, double* blocks, const GlNodeTables& tab,
-                  int n_sessions, int n_frames, int n_mels, int first_frame, int iters, long long ring_base, int ring_len,
-                  cudaStream_t st);
-constexpr int kMaxFramesPerPush = 16, kBlockRing = 32;
-struct EmitFrames { int n; long long index[kMaxFramesPerPush]; int pos[kMaxFramesPerPush]; int prev[kMaxFramesPerPush]; int ring_pos[kBlockRing]; long long ring_index[kBlockRing]; };
-int gl_emit_stream_run(const double* block_ring, const double* ola_window, double* lp_state, short* pcm, const LpCoefs& c,
-                       double norm_div, int first_frame, const EmitFrames& fr, cudaStream_t st);
-int dequantize_run(const double* labels, const double* medians, const double* taps, int radius, int smooth, int n_bins,
-                   int n_levels, long long n_rows, double* out, cudaStream_t st);
-int gl_emit_run(const double* blocks, const int* pos, const double* ola_window, double* v, double* states, double* zi,
-                double* zi_out, int carry_depth, const double* phi, const LpCoefs& c, double norm_div, short* pcm, double* filtered,
-                int n_sessions, int n_frames, int first_frame, long long n_out, int chunk, int n_chunks, cudaStream_t st);
-struct GlBatchTables { const double* window; const cplx* tw_half; const cplx* tw_full; const int* inv_idx; const double* inv_w; };
-int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int n_utt, int T, int n_mels, int iters,
-                 long long x_len, double* mx, short* pcm, cudaStream_t st);
-int exp_angle_run(const double* im, const double* re, long long n, double* out, cudaStream_t st);
-int logmel_run(const double* audio, long long n_audio, const double* window, const cplx* tw_half, const cplx* tw_full,
-               const double* mel, int n_mels, long long n_frames, int shift, int pad, double* out, cudaStream_t st);
-}  // namespace sgs
 
 static void make_twiddles(int n, std::vector<sgs::cplx>& half, std::vector<sgs::cplx>& full) {
     // half[t] = exp(-2 pi i t / (n/2)), t < n/2 ; full[k] = exp(-2 pi i k / n), k <= n/2 ; exact at the quadrant points

@@ -3,30 +3,9 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <vector>
-#include "common.cuh"
+#include "kernels.cuh"
 #include "../../include/sgs.h"
 
-namespace sgs {
-struct LdaGeom {
-    int n_bins, n_classes, n_features, n_levels;
-    int n_windows, n_channels, n_rows, first_row, order, step;
-    int smooth_radius;
-};
-int lda_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select,
-            const double* medians, const double* taps, double* labels, double* spec, int smooth, int n_sessions,
-            const LdaGeom& g, cudaStream_t st, const int* list, const int* list_count, long long list_cap);
-struct LdaTcGeom {
-    int n_windows, n_channels, n_rows, first_row, order, step, n_bins, n_features;
-    int tiles_per_session, n_tiles;
-    double eps;
-};
-int lda_tc_run(const double* feat, const float* Bmat, const double* Wt, const double* bias0, const double* chan_mean, double* bias,
-               const double* cls, const int* feat_chan, const int* feat_back, double* centre, const int* slice_bins, const double* wnorm,
-               double* labels, int* flags, int* list, int* count, long long n_frames_total, const LdaTcGeom& g, cudaStream_t st);
-int col_means_run(const double* x, long long n, long long row_stride, const int* select, int nf, double* xbar, cudaStream_t st);
-int dequantize_run(const double* labels, const double* medians, const double* taps, int radius, int smooth, int n_bins,
-                   int n_levels, long long n_rows, double* out, cudaStream_t st);
-}  // namespace sgs
 
 // tensor-core path geometry (csrc/lda_tc.cu)
 static const int kTcN = 128, kTcK = 160, kTcClasses = 9, kTcSlices = 3;

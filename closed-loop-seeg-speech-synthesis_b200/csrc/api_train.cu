@@ -1,17 +1,8 @@
 // C ABI for the training-side kernels (include/sgs.h).
 #include <vector>
-#include "common.cuh"
+#include "kernels.cuh"
 #include "../../include/sgs.h"
 
-namespace sgs {
-int quantize_run(const double* y, long long n, int ncol, const double* borders, int nint, double* q, cudaStream_t st);
-int colminmax_run(const double* y, long long n, int ncol, double* mn, double* mx, cudaStream_t st);
-int spearman_run(const double* x, long long n, int ncol, long long row_stride, const double* y, int ny, double* rho,
-                 double* colsum, cudaStream_t st);
-int col_means_run(const double* x, long long n, long long row_stride, const int* select, int nf, double* xbar, cudaStream_t st);
-int lda_stats_run(const double* x, long long n, long long row_stride, const int* select, int nf, const double* labels, int n_bins,
-                  int n_classes, double* xbar, double* G, double* sums, double* counts, const double* xbar_in, cudaStream_t st);
-}  // namespace sgs
 
 namespace {
 struct Bufs {

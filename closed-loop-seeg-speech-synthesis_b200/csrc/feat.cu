@@ -25,7 +25,7 @@
 //   pass 2        k_iir_stages<FEAT>: re-run each chunk from its slot, fused with window energy + log
 // `horizon` is chosen on the host from the actual transition matrix so that |A^horizon| is below the
 // requested tolerance (default 2^-70, far under one fp64 ulp of the state), see sgs/features.py.
-#include "feat.cuh"
+#include "kernels.cuh"
 
 namespace sgs {
 

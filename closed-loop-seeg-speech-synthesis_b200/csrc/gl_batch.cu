@@ -16,8 +16,7 @@
 // iteration reads it.  The windowed inverse transforms of the last 13 frames sit in a shared-memory ring so each
 // output sample is summed over its (up to 5) contributing frames in the reference's accumulation order.
 #include <math.h>
-#include "common.cuh"
-#include "fft.cuh"
+#include "kernels.cuh"
 
 namespace sgs {
 
@@ -25,13 +24,6 @@ constexpr int kBW = 8;                  // warps per CTA
 constexpr int kN = 800, kM = 400, kHopB = 160, kBinsB = 401, kOverlap = 5;
 constexpr int kRingB = kBW + kOverlap;  // 13 slots
 
-struct GlBatchTables {
-    const double* window;               // [800] periodic Hann
-    const cplx* tw_half;                // exp(-2 pi i t / 400)
-    const cplx* tw_full;                // exp(-2 pi i k / 800), k <= 400
-    const int* inv_idx;                 // [401][2]
-    const double* inv_w;                // [401][2]
-};
 
 __global__ void __launch_bounds__(kBW * 32)
 k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restrict__ x /*[B][x_len] in: noise, out: waveform*/,

@@ -19,21 +19,11 @@
 //              sequential 5x5 carry, final pass with clip + int16).
 #include <math.h>
 #include <stdlib.h>
-#include "common.cuh"
-#include "fft.cuh"
+#include "kernels.cuh"
 #include "exp_angle.cuh"
 
 namespace sgs {
 
-constexpr int kFft = 256, kHalf = 128, kHop = 160, kBlk = 480, kBins = 129;
-
-struct GlNodeTables {               // device pointers, built once per node configuration
-    const double* window;           // blackman(256)
-    const cplx* tw_full;            // exp(-2 pi i k / 256), k <= 128
-    const cplx* tw_t;               // [16][9] W128^(l k1) (register-FFT kernel, gl_blocks8.cuh)
-    const int* inv_idx;             // [129][2] mel index of each inverse-mel tap
-    const double* inv_w;            // [129][2] weight (0 where unused)
-};
 
 
 __device__ __forceinline__ double uniform01(unsigned long long seed, unsigned long long item, unsigned idx) {
@@ -119,8 +109,6 @@ k_gl_ola(const double* __restrict__ blocks, const int* __restrict__ pos, const d
 // ------------------------------------------------------------------------------------------------
 // order-ORD IIR (direct form II transposed, scipy.signal.lfilter) along each session's output stream
 // ------------------------------------------------------------------------------------------------
-constexpr int kLpMaxOrd = 8;
-struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
 
 template <int ORD>
 __device__ __forceinline__ double lp_step(double xin, double (&z)[ORD], const LpCoefs& c) {

@@ -14,7 +14,7 @@
 // Layout: W is repacked on upload to [bin][feature][class] so that the 9 class weights of one (bin, feature)
 // are contiguous and warp-uniform.  Block = 4 warps x 32 frames (lane = frame); warp w scores bins w, w+4, ...
 #include <math.h>
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace sgs {
 
@@ -22,11 +22,6 @@ constexpr int kLdaFrames = 32;
 constexpr int kLdaWarps = 4;
 constexpr int kMaxClasses = 9;
 
-struct LdaGeom {
-    int n_bins, n_classes, n_features, n_levels;
-    int n_windows, n_channels, n_rows, first_row, order, step;
-    int smooth_radius;
-};
 
 template <int KC>
 __global__ void __launch_bounds__(kLdaFrames * kLdaWarps)

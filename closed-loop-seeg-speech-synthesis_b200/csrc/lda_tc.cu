@@ -21,7 +21,7 @@
 //               warps 0-3        : epilogue - tcgen05.ld of the finished accumulator (thread = frame row), bias, per-bin
 //                                  argmax, near-tie flag, label store; overlaps the next tile's loads and MMAs
 #include <math.h>
-#include "common.cuh"
+#include "kernels.cuh"
 #include "tc.cuh"
 
 namespace sgs {
@@ -37,11 +37,6 @@ constexpr int kTileBytes = 2 * kBBytes;                 // packed A tile in HBM:
 constexpr int kTcTail = 256 + kTcN * 8 + 16 * 8;        // barriers + bias + per-bin weight norms
 constexpr int kTcSmem = 2 * kBBytes + kTcStages * kAStageBytes + kTcTail;
 
-struct LdaTcGeom {
-    int n_windows, n_channels, n_rows, first_row, order, step, n_bins, n_features;
-    int tiles_per_session, n_tiles;
-    double eps;                                         // relative error bound of the tensor-core score
-};
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     // K-major, no swizzle: start address, leading (K) byte offset, stride (row-group) byte offset, version 1

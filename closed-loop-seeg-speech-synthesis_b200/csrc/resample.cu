@@ -12,7 +12,7 @@
 // host derives `warm` from the largest pole radius; 910 samples for q = 3).  The first chunk of each pass starts from the
 // exact scipy initial state.  The backward pass writes only the samples decimation keeps.
 #include <math.h>
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace sgs {
 

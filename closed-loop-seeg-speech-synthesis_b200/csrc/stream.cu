@@ -11,19 +11,10 @@
 // One small launch per pushed chunk / frame; all state stays resident in device memory between calls.  The
 // filters run one thread per channel here: a 64-sample packet is ~15 us of serial work, latency not throughput.
 #include <math.h>
-#include "feat.cuh"
+#include "kernels.cuh"
 
 namespace sgs {
 
-constexpr int kSqRing = 256;       // per-channel history of y^2 (>= frame_size + largest sub-chunk)
-constexpr int kFeatRing = 32;      // per-channel history of log-power rows (>= order*step + 1)
-constexpr int kMaxFramesPerPush = 16;
-
-struct StreamFrames {              // frames completed by this push (host computes the schedule)
-    int n;
-    long long end[kMaxFramesPerPush];      // exclusive end, in real-sample coordinates (zero fill = negative)
-    long long index[kMaxFramesPerPush];    // running frame number k
-};
 
 template <int NB, typename TIn>
 __global__ void __launch_bounds__(128)
@@ -154,17 +145,6 @@ int dequantize_run(const double* labels, const double* medians, const double* ta
 
 // ---- GriffinLim node: overlap-add of the newest block(s) with the ones still in the ring, low-pass, int16 ----
 constexpr int kBlkLen = 480;
-constexpr int kBlockRing = 32;      // >= kMaxFramesPerPush + 4: a push writes all its blocks before the first hop is emitted
-constexpr int kLpMaxOrd = 8;
-struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
-struct EmitFrames {
-    int n;
-    long long index[kMaxFramesPerPush];    // frame number k
-    int pos[kMaxFramesPerPush];            // write head after frame k
-    int prev[kMaxFramesPerPush];           // write head before frame k
-    int ring_pos[kBlockRing];              // write head of the block stored in each ring slot (after this push)
-    long long ring_index[kBlockRing];      // its frame number (-1 = empty)
-};
 
 __global__ void __launch_bounds__(192)
 k_gl_emit_stream(const double* __restrict__ block_ring /*[kBlockRing][480]*/, const double* __restrict__ ola_window,

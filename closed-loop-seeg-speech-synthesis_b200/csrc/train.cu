@@ -13,7 +13,7 @@
 #include <vector>
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include <stdlib.h>
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace sgs {
 
@@ -264,8 +264,9 @@ int spearman_run(const double* x, long long n, int ncol, long long row_stride, c
 
 // xbar[nf] (global mean of the selected columns), G[nf][nf] = Xc^T Xc, sums[bin][class][nf], counts[bin][class]
 int col_means_run(const double* x, long long n, long long row_stride, const int* select, int nf, double* xbar, cudaStream_t st) {
-    int n_slices = (int)(n / 2048);
-    n_slices = n_slices < 1 ? 1 : (n_slices > 64 ? 64 : n_slices);
+    // enough row slices to fill the GPU (the decode path calls this on 1.9 M rows per step: 64 CTAs took 6.5 ms)
+    int n_slices = (int)(n / 256);
+    n_slices = n_slices < 1 ? 1 : (n_slices > 148 * 8 ? 148 * 8 : n_slices);
     double* p_col = nullptr;
     SGS_CUDA(cudaMallocAsync((void**)&p_col, sizeof(double) * n_slices * nf, st));
     k_colsum_partial<<<dim3(ceil_div(nf, 128), n_slices), 128, 0, st>>>(x, select, n, row_stride, nf, n_slices, p_col);
@@ -276,10 +277,6 @@ int col_means_run(const double* x, long long n, long long row_stride, const int*
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;
 }
-
-bool lda_stats_tc_supported(int nf, int n_bins, int n_classes);
-int lda_stats_tc_run(const double* x, long long n, long long row_stride, const int* select, int nf, const double* labels, int n_bins,
-                     int n_classes, const double* xbar, double* G, double* sums, double* counts, cudaStream_t st);
 
 int lda_stats_run(const double* x, long long n, long long row_stride, const int* select, int nf, const double* labels, int n_bins,
                   int n_classes, double* xbar, double* G, double* sums, double* counts, const double* xbar_in, cudaStream_t st) {

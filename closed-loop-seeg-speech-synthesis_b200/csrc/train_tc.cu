@@ -27,7 +27,7 @@
 //               all 4 warps: epilogue, tcgen05.ld -> 64-bit atomic adds.
 // k_tc_combine  integer accumulators -> G, class sums, counts in fp64.
 #include <math.h>
-#include "common.cuh"
+#include "kernels.cuh"
 #include "tc.cuh"
 
 namespace sgs {
