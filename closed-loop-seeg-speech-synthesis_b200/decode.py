@@ -8,6 +8,7 @@
                                 smoothing, node-semantics Griffin-Lim), which is what makes many-session
                                 throughput possible.  Set streaming=True to run the node graph instead.
     decode_sessions             many equally long sessions at once, device-resident (the throughput path).
+    session_shard               which sessions this rank decodes when one process per GPU shares a job (no collective).
 """
 import logging
 import pickle
@@ -111,6 +112,27 @@ class OfflineDecoder:
         if pinned_outputs:
             return out_spec.numpy(), out_audio.numpy()
         return out_spec.numpy().copy(), out_audio.numpy().copy()
+
+
+def session_shard(n_sessions, rank=None, world=None):
+    """[lo, hi) of the sessions this rank decodes when a job is spread over the GPUs of one box, one process per GPU:
+    sessions are independent end to end, so the decode path has no collective - every rank takes a contiguous, balanced
+    slice (sizes differ by at most one).  rank / world default to torch.distributed's, else RANK / WORLD_SIZE, else 0 / 1."""
+    import os
+    if rank is None or world is None:
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+    if rank is None or world is None:
+        rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    if not 0 <= rank < world:
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    base, extra = divmod(int(n_sessions), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
 
 
 def decode_sessions(decoder, eeg_sessions, seed=0):

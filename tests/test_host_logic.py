@@ -148,3 +148,40 @@ def test_receiver_flushes_when_a_forked_feeder_exits():
     p.start(); p.join()
     assert p.exitcode == 0
     assert sorted(rec.get_data()) == [-1, 0, 1, 2, 3, 4, 5, 6]
+
+
+def test_fused_chain_is_found_only_for_the_reference_wiring():
+    """sgs.chain.find_chain recognises decode.setup_decoder's graph (decode.py:152-183) and nothing else; no device needed."""
+    import pickle
+    import decode
+    from livenodes import Node, LambdaNode, Dequantization, LDASynthesis, ECogFeatCalc, GriffinLim
+    from sgs import chain
+    from sgs.training import PackedLDA
+    ests = []
+    for _ in range(3):
+        e = PackedLDA(); e.coef_ = np.zeros((9, 4)); e.intercept_ = np.zeros(9); e.classes_ = np.arange(9.0)
+        ests.append(e)
+    blob, med = pickle.dumps(ests), np.zeros((3, 9))
+    src = Node.Node(name='src', has_inputs=False)
+    decode.setup_decoder(src, 1024, blob, med, [], np.arange(4), include_soundcard=False, nb_mel_bins=3)
+    feat = src.output_classes[0].output_classes[0]
+    found = chain.find_chain(feat)
+    assert found is not None and [type(n).__name__ for n in found] == ['LDASynthesis', 'Dequantization', 'GriffinLimSynthesis']
+    os_env = __import__('os').environ
+    os_env['SGS_FUSED_CHAIN'] = '0'
+    try:
+        assert chain.find_chain(feat) is None
+    finally:
+        del os_env['SGS_FUSED_CHAIN']
+    # a node between LDA and dequantisation, or a second LDA consumer, is not the reference wiring
+    src2 = Node.Node(name='src2', has_inputs=False)
+    f2 = ECogFeatCalc.ECogFeatCalc(1024, 50, 10)(src2)
+    l2 = LDASynthesis.LDASynthesis(blob, select=np.arange(4))(f2)
+    mid = LambdaNode.LambdaNode(lambda f: f)(l2)
+    Dequantization.Dequantization(med)(mid)
+    assert chain.find_chain(f2) is None
+    src3 = Node.Node(name='src3', has_inputs=False)
+    f3 = ECogFeatCalc.ECogFeatCalc(1024, 50, 10)(src3)
+    LDASynthesis.LDASynthesis(blob, select=np.arange(4))(f3)
+    LDASynthesis.LDASynthesis(blob, select=np.arange(4))(f3)
+    assert chain.find_chain(f3) is None

@@ -84,3 +84,50 @@ def test_two_rank_gloo_allreduce_fit(tmp_path):
         assert np.abs(R['xbar'] - X.mean(0)).max() < 1e-12
         for b, e in enumerate(single):
             assert np.abs(R['coef%d' % b] - e.coef_).max() <= 1e-9 * np.abs(e.coef_).max()
+
+
+SHARD_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+import decode
+dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=int(os.environ['WORLD_SIZE']))
+out = {}
+for n in (0, 1, 2, 7, 256):
+    lo, hi = decode.session_shard(n)                       # rank / world from the process group
+    t = torch.tensor([lo, hi])
+    both = [torch.zeros(2, dtype=torch.long) for _ in range(dist.get_world_size())]
+    dist.all_gather(both, t)
+    out[str(n)] = [b.tolist() for b in both]
+# the bench's timing rule: the step time of the job is the MAX over ranks
+ms = torch.tensor([10.0 + dist.get_rank()], dtype=torch.float64)
+dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+out['max_ms'] = float(ms.item())
+if dist.get_rank() == 0:
+    json.dump(out, open(sys.argv[2], 'w'))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_session_sharding(tmp_path):
+    """Decode shards by session with no data-path collective: the ranks' slices partition the job exactly."""
+    import json
+    import subprocess
+    import decode
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, 'closed-loop-seeg-speech-synthesis_b200')
+    script = tmp_path / 'shard_worker.py'
+    script.write_text(SHARD_WORKER)
+    out = str(tmp_path / 'shards.json')
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29534', WORLD_SIZE='2')
+    procs = [subprocess.Popen([sys.executable, str(script), pkg, out], env=dict(env, RANK=str(r))) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    R = json.load(open(out))
+    for n in (0, 1, 2, 7, 256):
+        (lo0, hi0), (lo1, hi1) = R[str(n)]
+        assert lo0 == 0 and hi0 == lo1 and hi1 == n and abs((hi0 - lo0) - (hi1 - lo1)) <= 1
+    assert R['max_ms'] == 11.0
+    assert [decode.session_shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    with pytest.raises(ValueError):
+        decode.session_shard(4, 2, 2)
