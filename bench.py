@@ -29,7 +29,7 @@ METRIC = "sEEG channel-seconds decoded to audio per second"
 UNIT = "channel-seconds/s"
 N_CH, SR, DUR = 128, 2048, 600.0
 SESSIONS_PER_GPU = int(os.environ.get('SGS_BENCH_SESSIONS', '32'))
-E2E_SESSIONS = int(os.environ.get('SGS_BENCH_E2E_SESSIONS', '8'))
+E2E_SESSIONS = int(os.environ.get('SGS_BENCH_E2E_SESSIONS', '16'))
 WORKLOAD = ("config5: %d sessions/GPU x %d ch x %g s @ %d Hz, full decode (features+LDA+dequant+Griffin-Lim node, 8 iters)"
             % (SESSIONS_PER_GPU, N_CH, DUR, SR))
 FLOP_PER_SAMPLE = 99          # 3 gain sections x 5 + 21 monic sections x 4 fp64 operations
@@ -122,12 +122,15 @@ def run_ours(args):
     barrier()
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         out = step()
+        marks[k].record()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    step_ms = [(ev0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(args.steps)]
     launches = _lib.launch_count() - n0
     prof = {k: _lib.profile_read(k) for k in ('iir_init', 'iir_state', 'iir_carry', 'iir_feat', 'lda_tc', 'lda', 'gl_blocks', 'gl_ola', 'lowpass')}
     _lib.profile_enable(False)
@@ -209,6 +212,7 @@ def run_ours(args):
                                        "unit": "fp64 op/s", "frac": dp_ops / (iir_ms * 1e-3) / FP64_PEAK if iir_ms > 0 else None,
                                        "peak_source": "measured DFMA/s, tools/pipe_peak.cu"}},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "ms_each_step": [round(v, 3) for v in step_ms],
             "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
             "clocks": clocks_summary(clk_path, local),
         }
