@@ -1,5 +1,7 @@
 // C ABI for feature extraction (include/sgs.h).
 #include <math.h>
+#include <algorithm>
+#include <stdlib.h>
 #include <vector>
 #include "kernels.cuh"
 #include "../../include/sgs.h"
@@ -140,8 +142,73 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
     rc = stage_out(sf, feat, f_bytes, st);
     if (rc) { release(sx, st); return rc; }
 
-    // small per-call tables + carry scratch, stream-ordered
     const int ns = 2 * p->n_biquads;
+    // ---- balanced pieces (feat.cu:k_iir_pieces) when the zero-state horizon is short against the work of one CTA ---------------------
+    {
+        const long long G = (g.n_streams + 31) / 32;
+        int sms = 148;
+        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const char* env_p = getenv("SGS_FEAT_PIECES_P");                     // tests force a small piece count on small inputs
+        const long long P = (env_p && atoi(env_p) > 0) ? atoi(env_p) : 3LL * sms;   // 3 resident CTAs per SM saturate the FP64 pipe
+        long long piece_len = (G * n_samples + P - 1) / P;
+        piece_len = (piece_len + 63) / 64 * 64;
+        const char* env = getenv("SGS_FEAT_PIECES");
+        const bool want = !(env && env[0] == '0');
+        if (want && !apply_phi && n_chunks > 1 && horizon % 64 == 0 && piece_len >= 2LL * horizon && piece_len <= n_samples) {
+            std::vector<FeatSeg> segs;
+            std::vector<int> piece_first;
+            auto first_window_at = [&](long long t) {                        // first window whose start is >= t
+                return (int)(std::lower_bound(win_starts, win_starts + n_windows, t, [](int32_t a, long long b) { return (long long)a < b; }) - win_starts);
+            };
+            const long long total = G * n_samples;
+            for (long long b0 = 0; b0 < total; b0 += piece_len) {
+                piece_first.push_back((int)segs.size());
+                const long long b1 = std::min(total, b0 + piece_len);
+                long long pos = b0;
+                while (pos < b1) {
+                    const long long grp = pos / n_samples;
+                    long long t0 = pos - grp * n_samples;
+                    t0 = t0 / 64 * 64;                                        // segment starts on a batch boundary of its recording
+                    long long t1 = std::min(b1, (grp + 1) * n_samples) - grp * n_samples;
+                    const bool to_end = (grp + 1) * n_samples <= b1;
+                    if (!to_end) t1 = t1 / 64 * 64;
+                    FeatSeg sg;
+                    sg.group = (int)grp;
+                    sg.t_begin = t0;
+                    sg.warm_begin = t0 > horizon ? t0 - horizon : 0;
+                    sg.k_lo = t0 == 0 ? 0 : first_window_at(t0);
+                    sg.k_hi = to_end ? n_windows : first_window_at(t1);
+                    if (t1 > t0) segs.push_back(sg);
+                    pos = grp * n_samples + (to_end ? n_samples : std::max(t1, t0 + 1));
+                    if (!to_end) break;                                       // the rest of this group belongs to the next piece
+                }
+            }
+            piece_first.push_back((int)segs.size());
+            const int n_pieces = (int)piece_first.size() - 1;
+            const size_t seg_bytes = sizeof(FeatSeg) * segs.size(), pf_bytes = sizeof(int) * piece_first.size();
+            const size_t init_bytes = sizeof(double) * (size_t)ns * g.n_streams, slot_bytes = sizeof(double) * (size_t)ns * 32 * segs.size();
+            char* d_tab2 = nullptr;
+            double* d_state = nullptr;
+            const size_t pf_off = (seg_bytes + 15) & ~(size_t)15;
+            cudaError_t e2 = cudaMallocAsync((void**)&d_tab2, pf_off + pf_bytes, st);
+            if (e2 == cudaSuccess) e2 = cudaMallocAsync((void**)&d_state, init_bytes + slot_bytes, st);
+            if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(d_tab2, segs.data(), seg_bytes, cudaMemcpyHostToDevice, st);
+            if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(d_tab2 + pf_off, piece_first.data(), pf_bytes, cudaMemcpyHostToDevice, st);
+            if (e2 != cudaSuccess) { release(sx, st); release(sf, st); return cuda_fail(e2, "piece tables", __FILE__, __LINE__); }
+            // (both tables are far below the 64 KB that the runtime stages synchronously, so the vectors may go out of scope)
+            rc = feat_run_pieces(p->n_biquads, p->monic, sx.dev, x_is_f64 != 0, (double*)sf.dev, d_state, d_state + (size_t)ns * g.n_streams,
+                                 (const FeatSeg*)d_tab2, (const int*)(d_tab2 + pf_off), n_pieces, p->d_starts, p->d_zf, p->cf, g, st);
+            if (rc == SGS_OK) rc = finish_out(sf, st);
+            cudaFreeAsync(d_tab2, st);
+            cudaFreeAsync(d_state, st);
+            const bool sync2 = sf.host != nullptr;
+            release(sx, st);
+            release(sf, st);
+            if (rc == SGS_OK && sync2) SGS_CUDA(cudaStreamSynchronize(st));
+            return rc;
+        }
+    }
+    // small per-call tables + carry scratch, stream-ordered
     const size_t tab_bytes = sizeof(long long) * (n_chunks + 1) + sizeof(int) * (n_chunks + 1) + (apply_phi ? sizeof(double) * ns * ns : 0);
     const size_t carry_bytes = sizeof(double) * (size_t)n_chunks * ns * g.n_streams;      // state slot per chunk start
     char* d_tab = nullptr;

@@ -76,16 +76,20 @@ __device__ __forceinline__ void block_sync() { asm volatile("bar.sync 0;" ::: "m
 // Coefficients are compile-time offsets into the __grid_constant__ parameter block, so they reach the
 // FP64 pipe as uniform-register / constant operands: a DFMA with three distinct 64-bit REGISTER operands
 // only issues every 3 cycles on sm_100 (measured, tools/pipe_peak.cu), with a uniform operand every 2.
+// Where a segment's cascade state comes from and goes to: element i of this lane's stream sits at base[i * stride]
+// (base already includes the lane / stream offset); in == nullptr starts from the zero state.
+struct SegState { const double* in; long long in_stride; double* out; long long out_stride; };
+
 template <int NB, bool MONIC, int MODE, int RING, int STAGE, typename TIn>
 __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __restrict__ feat,
-                                          double* __restrict__ state, const int* __restrict__ starts,
+                                          const SegState ss, const int* __restrict__ starts,
                                           const double* __restrict__ zero_fill_resp, const FeatCoefs& cf,
-                                          const FeatGeom& g, double* __restrict__ smem, const int j,
+                                          const FeatGeom& g, double* __restrict__ smem, const int group, const bool at_stream_start,
                                           const long long t_begin, const int len, const int k_lo, const int k_hi) {
     constexpr int BPS = NB / kStages, FIRST = STAGE * BPS;
     constexpr bool LAST = STAGE == kStages - 1;
     const int lane = threadIdx.x & 31;
-    int stream = blockIdx.x * kStreamsPerBlock + lane;
+    int stream = group * kStreamsPerBlock + lane;
     const bool live = stream < g.n_streams;
     if (!live) stream = g.n_streams - 1;
     const int sess = stream / g.n_channels, ch = stream - sess * g.n_channels;
@@ -99,13 +103,11 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
     // state of this stage's sections for this lane's stream
     double z0[BPS], z1[BPS];
     {
-        const bool zero_state = (MODE == kModeState) && (j > 0 || t_begin != 0 /*truncated*/);
-        const double* sp = state + ((long long)j * (2 * NB)) * g.state_stride + stream;
 #pragma unroll
         for (int p = 0; p < BPS; ++p) {
             const int i = FIRST + p;
-            z0[p] = zero_state ? 0.0 : sp[(long long)(2 * i) * g.state_stride];
-            z1[p] = zero_state ? 0.0 : sp[(long long)(2 * i + 1) * g.state_stride];
+            z0[p] = ss.in ? ss.in[(long long)(2 * i) * ss.in_stride] : 0.0;
+            z1[p] = ss.in ? ss.in[(long long)(2 * i + 1) * ss.in_stride] : 0.0;
         }
     }
 
@@ -127,7 +129,7 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
     if (LAST && MODE == kModeFeat) {
         next_end = (int)((long long)starts[k_lo] + g.window_len - t_begin);
         if (k_lo + 1 < k_hi) after_end = (int)((long long)starts[k_lo + 1] + g.window_len - t_begin);
-        if (j == 0 && g.t_first < 0) {
+        if (at_stream_start && g.t_first < 0) {
             // online framing starts inside the warm-start zero fill of the last filter (FrameBuffer.py:95-98): its
             // response there is a session-independent table; seed the ring with its prefix sums
             zf_lo = g.t_first;
@@ -212,15 +214,23 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
     }
 
     if (MODE == kModeState && live) {
-        double* outp = state + ((long long)(j + 1) * (2 * NB)) * g.state_stride + stream;
 #pragma unroll
         for (int p = 0; p < BPS; ++p) {
             const int i = FIRST + p;
-            outp[(long long)(2 * i) * g.state_stride] = z0[p];
-            outp[(long long)(2 * i + 1) * g.state_stride] = z1[p];
+            ss.out[(long long)(2 * i) * ss.out_stride] = z0[p];
+            ss.out[(long long)(2 * i + 1) * ss.out_stride] = z1[p];
         }
     }
 }
+
+#define SGS_RUN_STAGE(S) run_stage<NB, MONIC, MODE, RING, S, TIn>(x, feat, ss, starts, zero_fill_resp, cf, g, smem, group, at_start, t_begin, len, k_lo, k_hi)
+#define SGS_DISPATCH_STAGE(rot)                                                                    \
+    switch (((threadIdx.x >> 5) + (rot)) & (kStages - 1)) {                                        \
+        case 0: SGS_RUN_STAGE(0); break;                                                           \
+        case 1: SGS_RUN_STAGE(1); break;                                                           \
+        case 2: SGS_RUN_STAGE(2); break;                                                           \
+        default: SGS_RUN_STAGE(3); break;                                                          \
+    }
 
 // grid = (ceil(streams/32), chunks); block = 4 warps = 4 pipeline stages.
 // FEAT mode: the last stage keeps a running prefix sum P of y^2 per stream and writes it to a ring in shared
@@ -233,12 +243,13 @@ k_iir_stages(const TIn* __restrict__ x, double* __restrict__ feat, double* __res
              const double* __restrict__ zero_fill_resp, const __grid_constant__ FeatCoefs cf,
              const __grid_constant__ FeatGeom g) {
     extern __shared__ double smem[];
-    const int j = blockIdx.y;
+    const int j = blockIdx.y, group = blockIdx.x;
     long long t_begin = bounds[j], t_end;
     int k_lo = 0, k_hi = 0;
+    bool truncated = false;
     if (MODE == kModeState) {
         t_end = bounds[j + 1];
-        if (t_end - g.horizon > t_begin) t_begin = t_end - g.horizon;      // truncated zero-state pass
+        if (t_end - g.horizon > t_begin) { t_begin = t_end - g.horizon; truncated = true; }   // truncated zero-state pass
     } else {
         k_lo = kfirst[j]; k_hi = kfirst[j + 1];
         if (k_lo >= k_hi) return;
@@ -246,15 +257,68 @@ k_iir_stages(const TIn* __restrict__ x, double* __restrict__ feat, double* __res
     }
     const int len = (int)(t_end - t_begin);
     // in STATE mode the host guarantees len % kBatch == 0 so that the end state is taken exactly at t_end
+    const int lane = threadIdx.x & 31;
+    int stream = group * kStreamsPerBlock + lane;
+    if (stream >= g.n_streams) stream = g.n_streams - 1;
+    double* slot_j = state + ((long long)j * (2 * NB)) * g.state_stride + stream;
+    SegState ss;
+    ss.in = (MODE == kModeState && (j > 0 || truncated)) ? nullptr : slot_j;
+    ss.in_stride = g.state_stride;
+    ss.out = slot_j + (long long)(2 * NB) * g.state_stride;
+    ss.out_stride = g.state_stride;
+    const bool at_start = j == 0;
     // rotate the stage -> warp (= scheduler) assignment with the block index so that co-resident CTAs do not
     // stack all their heaviest stages on the same scheduler
-    switch (((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & (kStages - 1)) {
-        case 0: run_stage<NB, MONIC, MODE, RING, 0, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
-        case 1: run_stage<NB, MONIC, MODE, RING, 1, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
-        case 2: run_stage<NB, MONIC, MODE, RING, 2, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
-        default: run_stage<NB, MONIC, MODE, RING, 3, TIn>(x, feat, state, starts, zero_fill_resp, cf, g, smem, j, t_begin, len, k_lo, k_hi); break;
+    SGS_DISPATCH_STAGE(blockIdx.x + blockIdx.y)
+}
+
+// ---- balanced pieces -------------------------------------------------------------------------------------------------------
+// The time lines of all stream groups are laid end to end and cut into P equal pieces, P a multiple of the SM count, one CTA
+// per piece: with (groups x chunks) CTAs the 148 SMs held 2 or 3 CTAs each and the kernel ran at the pace of the 3-CTA SMs
+// (SMs active 88 % of the time, profiles/ncu_iir_feat32_r01.txt; 37 sessions - 444 CTAs - took exactly as long as 32).  A piece
+// is one or two segments (the end of one group's recording and the start of the next one's).  A segment that does not start
+// at t = 0 gets its start state from the zero-state pass over the `horizon` samples before it (or, nearer than that to the
+// beginning, from the true initial state), written to its own slot seg_state[segment][2 NB][32].
+template <int NB, bool MONIC, int MODE, int RING, typename TIn>
+__global__ void __launch_bounds__(kStages * 32)
+k_iir_pieces(const TIn* __restrict__ x, double* __restrict__ feat, const double* __restrict__ init_state /*[2NB][streams]*/,
+             double* __restrict__ seg_state /*[segment][2NB][32]*/, const FeatSeg* __restrict__ segs, const int* __restrict__ piece_first,
+             const int* __restrict__ starts, const double* __restrict__ zero_fill_resp, const __grid_constant__ FeatCoefs cf,
+             const __grid_constant__ FeatGeom g) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    for (int si = piece_first[blockIdx.x]; si < piece_first[blockIdx.x + 1]; ++si) {
+        const FeatSeg sg = segs[si];
+        const int group = sg.group;
+        int stream = group * kStreamsPerBlock + lane;
+        if (stream >= g.n_streams) stream = g.n_streams - 1;
+        double* slot = seg_state + ((long long)si * (2 * NB)) * 32 + lane;
+        const double* init = init_state + stream;
+        SegState ss;
+        long long t_begin;
+        int len, k_lo = sg.k_lo, k_hi = sg.k_hi;
+        bool at_start;
+        if (MODE == kModeState) {
+            if (sg.t_begin == 0) continue;                                   // starts from the initial state: nothing to compute
+            t_begin = sg.warm_begin;
+            len = (int)(sg.t_begin - sg.warm_begin);
+            ss.in = sg.warm_begin == 0 ? init : nullptr; ss.in_stride = g.state_stride;
+            ss.out = slot; ss.out_stride = 32;
+            at_start = false;
+        } else {
+            if (k_lo >= k_hi) continue;
+            t_begin = sg.t_begin;
+            len = (int)((long long)starts[k_hi - 1] + g.window_len - t_begin);
+            ss.in = sg.t_begin == 0 ? init : slot; ss.in_stride = sg.t_begin == 0 ? g.state_stride : 32;
+            ss.out = nullptr; ss.out_stride = 0;
+            at_start = sg.t_begin == 0;
+        }
+        SGS_DISPATCH_STAGE(blockIdx.x)
+        __syncthreads();                                                     // the hand-off buffers and the ring are reused
     }
 }
+#undef SGS_DISPATCH_STAGE
+#undef SGS_RUN_STAGE
 
 // ------------------------------------------------------------------------------------------------
 // carry (exact mode): slot j+1 = Phi slot j + e_j for j >= 1, in place; slot 1 is already the true state
@@ -341,6 +405,64 @@ static void run_all(const TIn* x, double* feat, double* slots, const double* phi
             x, feat, slots, bounds, kfirst, starts, zf, cf, g);
     }
     SGS_LAUNCHED();
+}
+
+template <int NB, bool MONIC, int RING, typename TIn>
+static void run_pieces(const TIn* x, double* feat, double* init_state, double* seg_state, const FeatSeg* segs, const int* piece_first,
+                       int n_pieces, const int* starts, const double* zf, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
+    { ProfScope ps(kProfIirInit, st); k_iir_init<NB, TIn><<<ceil_div(g.n_streams, 128), 128, 0, st>>>(x, init_state, cf, g); }
+    SGS_LAUNCHED();
+    constexpr int hand_bytes = (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
+    constexpr int feat_bytes = hand_bytes + RING * 32 * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_iir_pieces<NB, MONIC, kModeFeat, RING, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, feat_bytes);
+        attr_set = true;
+    }
+    {
+        ProfScope ps(kProfIirState, st);
+        k_iir_pieces<NB, MONIC, kModeState, RING, TIn><<<n_pieces, kStages * 32, hand_bytes, st>>>(x, feat, init_state, seg_state, segs,
+                                                                                                  piece_first, starts, zf, cf, g);
+    }
+    SGS_LAUNCHED();
+    {
+        ProfScope ps(kProfIirFeat, st);
+        k_iir_pieces<NB, MONIC, kModeFeat, RING, TIn><<<n_pieces, kStages * 32, feat_bytes, st>>>(x, feat, init_state, seg_state, segs,
+                                                                                                 piece_first, starts, zf, cf, g);
+    }
+    SGS_LAUNCHED();
+}
+
+template <typename TIn>
+static int run_pieces_typed(int n_biquads, bool monic, const TIn* x, double* feat, double* init_state, double* seg_state,
+                            const FeatSeg* segs, const int* piece_first, int n_pieces, const int* starts, const double* zf,
+                            const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
+#define SGS_RUN(NB, M, RING) run_pieces<NB, M, RING, TIn>(x, feat, init_state, seg_state, segs, piece_first, n_pieces, starts, zf, cf, g, st)
+#define SGS_PICK(NB, M)                                             \
+    do {                                                            \
+        if (g.window_len + kBatch + 1 <= 128) SGS_RUN(NB, M, 128);  \
+        else SGS_RUN(NB, M, 256);                                   \
+    } while (0)
+    if (g.window_len + kBatch + 1 > 256) { set_error("window_len %d too long (max %d)", g.window_len, 255 - kBatch); return SGS_ERR_UNSUPPORTED; }
+    if (n_biquads == 24 && monic) SGS_PICK(24, true);
+    else if (n_biquads == 24) SGS_PICK(24, false);
+    else if (n_biquads == 16 && monic) SGS_PICK(16, true);
+    else if (n_biquads == 16) SGS_PICK(16, false);
+    else { set_error("unsupported biquad count %d (16 or 24)", n_biquads); return SGS_ERR_UNSUPPORTED; }
+#undef SGS_PICK
+#undef SGS_RUN
+    SGS_CUDA(cudaGetLastError());
+    return SGS_OK;
+}
+
+int feat_run_pieces(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* init_state, double* seg_state,
+                    const FeatSeg* segs, const int* piece_first, int n_pieces, const int* starts, const double* zf,
+                    const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
+    if (x_is_f64)
+        return run_pieces_typed<double>(n_biquads, monic, (const double*)x, feat, init_state, seg_state, segs, piece_first, n_pieces,
+                                        starts, zf, cf, g, st);
+    return run_pieces_typed<float>(n_biquads, monic, (const float*)x, feat, init_state, seg_state, segs, piece_first, n_pieces,
+                                   starts, zf, cf, g, st);
 }
 
 template <typename TIn>

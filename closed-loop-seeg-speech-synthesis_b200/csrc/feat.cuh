@@ -38,4 +38,12 @@ struct FeatGeom {
     int state_stride;                // = n_streams (carry layout [chunk][state][stream])
 };
 
+// One segment of a balanced work piece (k_iir_pieces, feat.cu).
+struct FeatSeg {
+    int group;                  // stream group (32 streams)
+    int k_lo, k_hi;             // windows owned: those that START inside the segment
+    long long t_begin;          // first sample of the segment
+    long long warm_begin;       // STATE pass: first sample of the warm-up run (0 = from the true initial state)
+};
+
 }  // namespace sgs

@@ -95,3 +95,28 @@ def test_device_resident_tensors():
     st = fe.stack(lp)
     want = O.herff2016_b(x.astype(np.float64), sr)
     assert np.abs(st.cpu().numpy() - want).max() < TOL
+
+
+@pytest.mark.parametrize('online', [False, True])
+def test_balanced_pieces_equal_chunked_scan(online, monkeypatch):
+    """The piece decomposition (time lines of all stream groups laid end to end, cut into equal pieces, one or two
+    segments per CTA) gives the features of the (group x chunk) decomposition and of the oracle."""
+    import torch
+    sr, n_ch, seconds, n_sess = 1024, 12, 150.0, 5                       # 60 streams = 2 groups, the second one partial
+    xs = np.stack([synth.seeg_session(60 + s, n_ch, sr, seconds) for s in range(n_sess)])
+    fe = FeatureExtractor(sr)
+    xd = torch.from_numpy(xs).cuda()
+    monkeypatch.setenv('SGS_FEAT_PIECES', '0')
+    ref = fe.log_power(xd, online=online, chunks=3).cpu().numpy()
+    monkeypatch.setenv('SGS_FEAT_PIECES', '1')
+    for pieces in ('5', '4', '3'):                                       # pieces straddling the group boundary or not
+        monkeypatch.setenv('SGS_FEAT_PIECES_P', pieces)
+        got = fe.log_power(xd, online=online, chunks=3).cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-10                            # prefix-sum re-basing points differ between the two
+    if online:
+        want = O.ecog_feat_calc(xs[3].astype(np.float64), sr, 50, 10, 4, 5, 50, 32)         # stacked rows: tap 4 = the frame itself
+        assert np.abs(got[3] - want[:, 4::5]).max() < 1e-9
+    else:
+        want = O.herff2016_b(xs[3].astype(np.float64), sr, skip_stacking=True)
+        assert np.abs(got[3] - want).max() < 1e-9
