@@ -352,4 +352,64 @@ int sgs_feat_stream_push(sgs_feat_stream* s, const void* x, int x_is_f64, int n,
     return SGS_OK;
 }
 
+/* ---- filtering FrameBuffer node (livenodes/FrameBuffer.py:86-143): one SOS cascade, state resident between chunks ---- */
+struct sgs_sos_stream {
+    sgs::SosCoefs cf;
+    int n_channels = 0, warm_start = 0;
+    bool first = true;
+    double *d_z = nullptr, *d_y = nullptr;
+    void* d_x = nullptr;
+    size_t cap = 0;                         // samples the staging buffers hold
+};
+
+void sgs_sos_stream_destroy(sgs_sos_stream* s) {
+    if (!s) return;
+    cudaFree(s->d_z); cudaFree(s->d_y); cudaFree(s->d_x);
+    delete s;
+}
+
+int sgs_sos_stream_create(sgs_sos_stream** stream_out, const double* sos, const double* zi, int n_sections, int n_channels,
+                          int warm_start) {
+    using namespace sgs;
+    SGS_ARG(stream_out && sos && zi, "NULL argument");
+    SGS_ARG(n_sections >= 1 && n_sections <= kSosMaxSections && n_channels >= 1, "1..%d sections, >= 1 channel", kSosMaxSections);
+    sgs_sos_stream* s = new sgs_sos_stream();
+    memset(&s->cf, 0, sizeof(s->cf));
+    s->cf.n_sections = n_sections; s->n_channels = n_channels; s->warm_start = warm_start ? 1 : 0;
+    for (int k = 0; k < n_sections; ++k) {
+        if (sos[k * 6 + 3] != 1.0) { delete s; set_error("sos section %d is not normalised (a0 = %g)", k, sos[k * 6 + 3]); return SGS_ERR_ARG; }
+        s->cf.c[k][0] = sos[k * 6 + 0]; s->cf.c[k][1] = sos[k * 6 + 1]; s->cf.c[k][2] = sos[k * 6 + 2];
+        s->cf.c[k][3] = sos[k * 6 + 4]; s->cf.c[k][4] = sos[k * 6 + 5];
+        s->cf.zi[k][0] = zi[k * 2]; s->cf.zi[k][1] = zi[k * 2 + 1];
+    }
+    cudaError_t e = cudaMalloc((void**)&s->d_z, sizeof(double) * 2 * n_sections * n_channels);
+    if (e != cudaSuccess) { sgs_sos_stream_destroy(s); return cuda_fail(e, "filter state", __FILE__, __LINE__); }
+    *stream_out = s;
+    return SGS_OK;
+}
+
+/* x[n][n_channels] (host, float32 or float64) -> y[n][n_channels] float64 (host): sosfilt with the state carried from the
+ * previous push; the first push starts from zi (warm start) or zi * x[0] (cold start).  Synchronous. */
+int sgs_sos_stream_push(sgs_sos_stream* s, const void* x, int x_is_f64, int n, double* y, void* stream) {
+    using namespace sgs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SGS_ARG(s && x && y && n >= 1, "bad arguments");
+    const size_t count = (size_t)n * s->n_channels;
+    if (s->cap < count) {
+        SGS_CUDA(cudaStreamSynchronize(st));
+        cudaFree(s->d_x); cudaFree(s->d_y);
+        s->d_x = nullptr; s->d_y = nullptr; s->cap = 0;
+        SGS_CUDA(cudaMalloc(&s->d_x, count * 8 * 2));
+        SGS_CUDA(cudaMalloc((void**)&s->d_y, count * 8 * 2));
+        s->cap = count * 2;
+    }
+    SGS_CUDA(cudaMemcpyAsync(s->d_x, x, count * (x_is_f64 ? 8 : 4), cudaMemcpyDefault, st));
+    int rc = sos_stream_run(s->d_x, x_is_f64 != 0, n, s->n_channels, s->d_z, s->d_y, s->first ? 1 : 0, s->warm_start, s->cf, st);
+    if (rc != SGS_OK) return rc;
+    s->first = false;
+    SGS_CUDA(cudaMemcpyAsync(y, s->d_y, count * 8, cudaMemcpyDefault, st));
+    SGS_CUDA(cudaStreamSynchronize(st));
+    return SGS_OK;
+}
+
 }  // extern "C"

@@ -33,6 +33,11 @@ int feat_stream_run(int n_biquads, const void* x, bool x_is_f64, int n, int n_ch
                     double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int frame_size, int order, int step,
                     double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st);
 
+constexpr int kSosMaxSections = 8;
+struct SosCoefs { double c[kSosMaxSections][5]; double zi[kSosMaxSections][2]; int n_sections; };   // b0 b1 b2 a1 a2; sosfilt_zi
+int sos_stream_run(const void* x, bool x_is_f64, int n, int n_channels, double* z, double* y, int first, int warm_start,
+                   const SosCoefs& cf, cudaStream_t st);
+
 // ---- LDA decode (lda.cu, lda_tc.cu) and dequantisation (stream.cu) ---------------------------------------------------------------
 struct LdaGeom {
     int n_bins, n_classes, n_features, n_levels;

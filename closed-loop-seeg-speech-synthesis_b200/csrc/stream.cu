@@ -109,6 +109,54 @@ int feat_stream_run(int n_biquads, const void* x, bool x_is_f64, int n, int n_ch
     return SGS_OK;
 }
 
+// ---- filtering FrameBuffer (livenodes/FrameBuffer.py:86-143): one sosfilt cascade with carried state -------------------------------
+// thread = channel; scipy's _sosfilt recurrence with separate multiplies and adds (y = b0 x + z0; z0 = b1 x - a1 y + z1;
+// z1 = b2 x - a2 y), sections inner loop, samples outer.  first != 0: the state starts from zi (warm start) or zi * x[0] (cold).
+template <typename TIn>
+__global__ void __launch_bounds__(128)
+k_sos_stream(const TIn* __restrict__ x, int n, int n_channels, double* __restrict__ z /*[2*sections][C]*/, double* __restrict__ y,
+             int first, int warm_start, const __grid_constant__ SosCoefs cf) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_channels) return;
+    double z0[kSosMaxSections], z1[kSosMaxSections];
+    const double x0 = (double)x[c];
+#pragma unroll
+    for (int s = 0; s < kSosMaxSections; ++s) {
+        if (s < cf.n_sections) {
+            z0[s] = first ? (warm_start ? cf.zi[s][0] : cf.zi[s][0] * x0) : z[(2 * s) * n_channels + c];
+            z1[s] = first ? (warm_start ? cf.zi[s][1] : cf.zi[s][1] * x0) : z[(2 * s + 1) * n_channels + c];
+        } else { z0[s] = 0.0; z1[s] = 0.0; }
+    }
+    for (int t = 0; t < n; ++t) {
+        double v = (double)x[(long long)t * n_channels + c];
+#pragma unroll
+        for (int s = 0; s < kSosMaxSections; ++s) {
+            if (s < cf.n_sections) {
+                const double out = __dadd_rn(__dmul_rn(cf.c[s][0], v), z0[s]);
+                z0[s] = __dadd_rn(__dadd_rn(__dmul_rn(cf.c[s][1], v), -__dmul_rn(cf.c[s][3], out)), z1[s]);
+                z1[s] = __dadd_rn(__dmul_rn(cf.c[s][2], v), -__dmul_rn(cf.c[s][4], out));
+                v = out;
+            }
+        }
+        y[(long long)t * n_channels + c] = v;
+    }
+#pragma unroll
+    for (int s = 0; s < kSosMaxSections; ++s) {
+        if (s < cf.n_sections) { z[(2 * s) * n_channels + c] = z0[s]; z[(2 * s + 1) * n_channels + c] = z1[s]; }
+    }
+}
+
+int sos_stream_run(const void* x, bool x_is_f64, int n, int n_channels, double* z, double* y, int first, int warm_start,
+                   const SosCoefs& cf, cudaStream_t st) {
+    ProfScope ps(kProfStream, st);
+    const int grid = ceil_div(n_channels, 128);
+    if (x_is_f64) k_sos_stream<double><<<grid, 128, 0, st>>>((const double*)x, n, n_channels, z, y, first, warm_start, cf);
+    else k_sos_stream<float><<<grid, 128, 0, st>>>((const float*)x, n, n_channels, z, y, first, warm_start, cf);
+    SGS_LAUNCHED();
+    SGS_CUDA(cudaGetLastError());
+    return SGS_OK;
+}
+
 // ---- Dequantization node: medians lookup + 5-tap smoothing across bins ---------------------------------------
 __global__ void k_dequantize(const double* __restrict__ labels, const double* __restrict__ medians,
                              const double* __restrict__ taps, int radius, int smooth, int n_bins, int n_levels,

@@ -88,6 +88,16 @@ void sgs_feat_stream_destroy(sgs_feat_stream* s);
 int sgs_feat_stream_push(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
                          const int64_t* frame_index, int n_frames, double* out, void* stream);
 
+/* Filtering FrameBuffer node (livenodes/FrameBuffer.py:86-143): one scipy.signal.sosfilt cascade (<= 8 sections) over all
+ * channels with the state resident between chunks.  sos[n_sections][6], zi[n_sections][2] = sosfilt_zi(sos); the first push
+ * starts from zi (warm_start, FrameBuffer.py:95-98 then pushes its zero fill through the same stream) or from zi * x[0]
+ * (cold start, FrameBuffer.py:90-92).  y[n][n_channels] float64 = the filtered chunk.  Synchronous. */
+typedef struct sgs_sos_stream sgs_sos_stream;
+int sgs_sos_stream_create(sgs_sos_stream** stream_out, const double* sos, const double* zi, int n_sections, int n_channels,
+                          int warm_start);
+void sgs_sos_stream_destroy(sgs_sos_stream* s);
+int sgs_sos_stream_push(sgs_sos_stream* s, const void* x, int x_is_f64, int n, double* y, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Per-mel-bin LDA decoding + dequantisation (+ optional smoothing across bins).
  * Replaces: 40 x sklearn LinearDiscriminantAnalysis.predict per frame (livenodes/LDASynthesis.py:25-26),

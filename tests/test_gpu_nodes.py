@@ -247,3 +247,38 @@ def test_config2_streaming_chain_matches_oracle():
     assert np.array_equal(spec, ws)
     d = np.abs(audio.astype(int) - wp.astype(int))
     assert audio.shape == wp.shape and d.max() <= 1 and (d > 0).mean() < 2e-3
+
+
+@pytest.mark.parametrize('warm_start', [False, True])
+@pytest.mark.parametrize('chunk', [16, 100, 5000])
+def test_filtering_framebuffer_matches_scipy(warm_start, chunk):
+    """FrameBuffer(filter_coefficients=sos) (livenodes/FrameBuffer.py:86-177): causal sosfilt with carried state on the device,
+    cold start (zi * first sample) or warm start (unit zi, zero fill pushed through the filter first), then framing with the
+    reference's rounded fractional shifts.  Checked against scipy.signal.sosfilt on the whole recording."""
+    from scipy.signal import iirfilter, sosfilt, sosfilt_zi
+    from livenodes import FrameBuffer
+    sr, n_ch = 1024, 7
+    x = synth.seeg_session(9, n_ch, sr, 6.0).astype(np.float64)
+    sos = iirfilter(8, [70 / (sr / 2), 170 / (sr / 2)], btype='band', ftype='butter', output='sos')
+    fb = FrameBuffer.FrameBuffer(50, 10, sr, filter_coefficients=sos, warm_start=warm_start)
+    frames = []
+    fb.add_output(lambda f: frames.append(np.array(f, copy=True)))
+    for i in range(0, len(x), chunk):
+        fb.add_data(x[i:i + chunk])
+    fs = int(0.05 * sr)
+    zi = np.repeat(sosfilt_zi(sos)[:, :, None], n_ch, axis=2)
+    if warm_start:
+        fill = fs - int(0.01 * sr)
+        y, _ = sosfilt(sos, np.vstack([np.zeros((fill, n_ch)), x]), axis=0, zi=zi)
+    else:
+        y, _ = sosfilt(sos, x, axis=0, zi=zi * x[0])
+    first_ms = fs / float(sr) * 1000.0
+    want, k, e = [], 0, fs
+    while e <= len(y):
+        want.append(y[e - fs:e])
+        k += 1
+        e = round(((first_ms + k * 10.0) / 1000.0) * float(sr))
+    assert len(frames) == len(want) and len(frames) > 550
+    got, want = np.array(frames), np.array(want)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
