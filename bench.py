@@ -51,16 +51,18 @@ def clocks_sampler(path):
     q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        return subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '200'],
+        return subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
                                 stdout=open(path, 'w'), stderr=subprocess.DEVNULL)
     except OSError:
         return None
 
 
-def clocks_summary(path, device_index):
+def clocks_summary(path, device_index, skip_lines=0):
     sm, mx, reasons = [], 0.0, set()
     try:
-        for line in open(path):
+        for i, line in enumerate(open(path)):
+            if i < skip_lines:
+                continue
             f = [c.strip() for c in line.split(',')]
             if len(f) < 9 or f[0] != str(device_index):
                 continue
@@ -113,13 +115,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi's own start-up (NVML initialisation, a few hundred ms) otherwise
+    # lands on the first timed step and stalls its launches; only samples taken inside the timed region are used
+    clk_path = os.path.join(tempfile.gettempdir(), 'sgs_clocks_%d.csv' % rank)
+    sampler = clocks_sampler(clk_path) if rank == 0 else None
     for _ in range(args.warmup):
         out = step()
     del out
-    clk_path = os.path.join(tempfile.gettempdir(), 'sgs_clocks_%d.csv' % rank)
-    sampler = clocks_sampler(clk_path) if rank == 0 else None
+    if sampler is not None:
+        torch.cuda.synchronize()
+        t_wait = time.time()
+        while (not os.path.exists(clk_path) or os.path.getsize(clk_path) == 0) and time.time() - t_wait < 5.0:
+            time.sleep(0.05)
     _lib.profile_enable(True)
     barrier()
+    clk_skip = sum(1 for _ in open(clk_path)) if sampler is not None and os.path.exists(clk_path) else 0
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -215,7 +225,7 @@ def run_ours(args):
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "ms_each_step": [round(v, 3) for v in step_ms],
             "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
-            "clocks": clocks_summary(clk_path, local),
+            "clocks": clocks_summary(clk_path, local, clk_skip),
         }
         line["cpu_baseline"] = cpu_baseline_sample()
         line["latency"] = latency_leg() if world == 1 and not args.no_latency else None

@@ -149,7 +149,7 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
         int sms = 148;
         { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
         const char* env_p = getenv("SGS_FEAT_PIECES_P");                     // tests force a small piece count on small inputs
-        const long long P = (env_p && atoi(env_p) > 0) ? atoi(env_p) : 3LL * sms;   // 3 resident CTAs per SM saturate the FP64 pipe
+        const long long P = (env_p && atoi(env_p) > 0) ? atoi(env_p) : 4LL * sms;   // one CTA per SM, one pipeline per scheduler (feat.cu)
         long long piece_len = (G * n_samples + P - 1) / P;
         piece_len = (piece_len + 63) / 64 * 64;
         const char* env = getenv("SGS_FEAT_PIECES");

@@ -70,7 +70,8 @@ constexpr int kStages = 4;                      // warps per CTA = pipeline stag
 constexpr int kBatch = 16;                      // samples handed from stage to stage per iteration
 constexpr int kStreamsPerBlock = 32;            // lane = stream
 
-__device__ __forceinline__ void block_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+// barrier among the 4 stage warps of one pipeline (named barrier `id`, 128 threads; id 0 when the CTA is one pipeline)
+__device__ __forceinline__ void pipe_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // One pipeline stage = BPS consecutive biquads of the cascade, run by one warp for 32 streams.
 // Coefficients are compile-time offsets into the __grid_constant__ parameter block, so they reach the
@@ -84,8 +85,9 @@ template <int NB, bool MONIC, int MODE, int RING, int STAGE, typename TIn>
 __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __restrict__ feat,
                                           const SegState ss, const int* __restrict__ starts,
                                           const double* __restrict__ zero_fill_resp, const FeatCoefs& cf,
-                                          const FeatGeom& g, double* __restrict__ smem, const int group, const bool at_stream_start,
-                                          const long long t_begin, const int len, const int k_lo, const int k_hi) {
+                                          const FeatGeom& g, double* __restrict__ smem, const int bar_id, const int group,
+                                          const bool at_stream_start, const long long t_begin, const int len, const int k_lo,
+                                          const int k_hi) {
     constexpr int BPS = NB / kStages, FIRST = STAGE * BPS;
     constexpr bool LAST = STAGE == kStages - 1;
     const int lane = threadIdx.x & 31;
@@ -210,7 +212,7 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
                 }
             }
         }
-        block_sync();
+        pipe_sync(bar_id);
     }
 
     if (MODE == kModeState && live) {
@@ -223,9 +225,9 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
     }
 }
 
-#define SGS_RUN_STAGE(S) run_stage<NB, MONIC, MODE, RING, S, TIn>(x, feat, ss, starts, zero_fill_resp, cf, g, smem, group, at_start, t_begin, len, k_lo, k_hi)
-#define SGS_DISPATCH_STAGE(rot)                                                                    \
-    switch (((threadIdx.x >> 5) + (rot)) & (kStages - 1)) {                                        \
+#define SGS_RUN_STAGE(S) run_stage<NB, MONIC, MODE, RING, S, TIn>(x, feat, ss, starts, zero_fill_resp, cf, g, smem_p, bar_id, group, at_start, t_begin, len, k_lo, k_hi)
+#define SGS_DISPATCH_STAGE(stage_warp, rot)                                                        \
+    switch (((stage_warp) + (rot)) & (kStages - 1)) {                                              \
         case 0: SGS_RUN_STAGE(0); break;                                                           \
         case 1: SGS_RUN_STAGE(1); break;                                                           \
         case 2: SGS_RUN_STAGE(2); break;                                                           \
@@ -267,9 +269,11 @@ k_iir_stages(const TIn* __restrict__ x, double* __restrict__ feat, double* __res
     ss.out = slot_j + (long long)(2 * NB) * g.state_stride;
     ss.out_stride = g.state_stride;
     const bool at_start = j == 0;
+    double* smem_p = smem;
+    const int bar_id = 0;
     // rotate the stage -> warp (= scheduler) assignment with the block index so that co-resident CTAs do not
     // stack all their heaviest stages on the same scheduler
-    SGS_DISPATCH_STAGE(blockIdx.x + blockIdx.y)
+    SGS_DISPATCH_STAGE(threadIdx.x >> 5, blockIdx.x + blockIdx.y)
 }
 
 // ---- balanced pieces -------------------------------------------------------------------------------------------------------
@@ -279,15 +283,25 @@ k_iir_stages(const TIn* __restrict__ x, double* __restrict__ feat, double* __res
 // is one or two segments (the end of one group's recording and the start of the next one's).  A segment that does not start
 // at t = 0 gets its start state from the zero-state pass over the `horizon` samples before it (or, nearer than that to the
 // beginning, from the true initial state), written to its own slot seg_state[segment][2 NB][32].
-template <int NB, bool MONIC, int MODE, int RING, typename TIn>
-__global__ void __launch_bounds__(kStages * 32)
+// PIPES pipelines per CTA: pipeline p = warps {p, p + PIPES, p + 2 PIPES, p + 3 PIPES}.  With PIPES = 4 the four stage warps
+// of a pipeline have warp indices congruent mod 4, i.e. they share one of the SM's four schedulers: a stage waiting at the
+// pipeline's barrier hands its issue slots to exactly the stage it is waiting for, instead of idling a scheduler while
+// another one is overloaded (the per-batch barrier was the largest stall with one stage per scheduler).
+template <int NB, bool MONIC, int MODE, int RING, int PIPES, typename TIn>
+__global__ void __launch_bounds__(PIPES * kStages * 32, 1)
 k_iir_pieces(const TIn* __restrict__ x, double* __restrict__ feat, const double* __restrict__ init_state /*[2NB][streams]*/,
              double* __restrict__ seg_state /*[segment][2NB][32]*/, const FeatSeg* __restrict__ segs, const int* __restrict__ piece_first,
-             const int* __restrict__ starts, const double* __restrict__ zero_fill_resp, const __grid_constant__ FeatCoefs cf,
+             int n_pieces, const int* __restrict__ starts, const double* __restrict__ zero_fill_resp, const __grid_constant__ FeatCoefs cf,
              const __grid_constant__ FeatGeom g) {
     extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31;
-    for (int si = piece_first[blockIdx.x]; si < piece_first[blockIdx.x + 1]; ++si) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pipe = warp % PIPES, stage_warp = warp / PIPES;
+    const int piece = blockIdx.x * PIPES + pipe;
+    if (piece >= n_pieces) return;
+    constexpr int pipe_doubles = (kStages - 1) * 2 * kBatch * 32 + (MODE == kModeFeat ? RING * 32 : 0);
+    double* smem_p = smem + (size_t)pipe * pipe_doubles;
+    const int bar_id = PIPES > 1 ? 1 + pipe : 0;
+    for (int si = piece_first[piece]; si < piece_first[piece + 1]; ++si) {
         const FeatSeg sg = segs[si];
         const int group = sg.group;
         int stream = group * kStreamsPerBlock + lane;
@@ -313,8 +327,8 @@ k_iir_pieces(const TIn* __restrict__ x, double* __restrict__ feat, const double*
             ss.out = nullptr; ss.out_stride = 0;
             at_start = sg.t_begin == 0;
         }
-        SGS_DISPATCH_STAGE(blockIdx.x)
-        __syncthreads();                                                     // the hand-off buffers and the ring are reused
+        SGS_DISPATCH_STAGE(stage_warp, piece)
+        pipe_sync(bar_id);                                                   // the hand-off buffers and the ring are reused
     }
 }
 #undef SGS_DISPATCH_STAGE
@@ -407,28 +421,32 @@ static void run_all(const TIn* x, double* feat, double* slots, const double* phi
     SGS_LAUNCHED();
 }
 
+constexpr int kPipes = 4;               // pipelines per CTA (see k_iir_pieces)
+
 template <int NB, bool MONIC, int RING, typename TIn>
 static void run_pieces(const TIn* x, double* feat, double* init_state, double* seg_state, const FeatSeg* segs, const int* piece_first,
                        int n_pieces, const int* starts, const double* zf, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
     { ProfScope ps(kProfIirInit, st); k_iir_init<NB, TIn><<<ceil_div(g.n_streams, 128), 128, 0, st>>>(x, init_state, cf, g); }
     SGS_LAUNCHED();
-    constexpr int hand_bytes = (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
-    constexpr int feat_bytes = hand_bytes + RING * 32 * (int)sizeof(double);
+    constexpr int hand_bytes = kPipes * (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
+    constexpr int feat_bytes = hand_bytes + kPipes * RING * 32 * (int)sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_iir_pieces<NB, MONIC, kModeFeat, RING, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, feat_bytes);
+        cudaFuncSetAttribute(k_iir_pieces<NB, MONIC, kModeFeat, RING, kPipes, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, feat_bytes);
+        cudaFuncSetAttribute(k_iir_pieces<NB, MONIC, kModeState, RING, kPipes, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, hand_bytes);
         attr_set = true;
     }
+    const int grid = ceil_div(n_pieces, kPipes);
     {
         ProfScope ps(kProfIirState, st);
-        k_iir_pieces<NB, MONIC, kModeState, RING, TIn><<<n_pieces, kStages * 32, hand_bytes, st>>>(x, feat, init_state, seg_state, segs,
-                                                                                                  piece_first, starts, zf, cf, g);
+        k_iir_pieces<NB, MONIC, kModeState, RING, kPipes, TIn><<<grid, kPipes * kStages * 32, hand_bytes, st>>>(
+            x, feat, init_state, seg_state, segs, piece_first, n_pieces, starts, zf, cf, g);
     }
     SGS_LAUNCHED();
     {
         ProfScope ps(kProfIirFeat, st);
-        k_iir_pieces<NB, MONIC, kModeFeat, RING, TIn><<<n_pieces, kStages * 32, feat_bytes, st>>>(x, feat, init_state, seg_state, segs,
-                                                                                                 piece_first, starts, zf, cf, g);
+        k_iir_pieces<NB, MONIC, kModeFeat, RING, kPipes, TIn><<<grid, kPipes * kStages * 32, feat_bytes, st>>>(
+            x, feat, init_state, seg_state, segs, piece_first, n_pieces, starts, zf, cf, g);
     }
     SGS_LAUNCHED();
 }
