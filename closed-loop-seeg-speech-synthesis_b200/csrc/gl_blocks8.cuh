@@ -24,6 +24,7 @@ constexpr int kG8RowStride = 9;                       // 8 entries + 1 pad: conf
 constexpr int kG8BufCplx = 16 * kG8RowStride;         // one group's transposition buffer (complex entries)
 constexpr int kG8BlockDoubles = 2 * kG8BufCplx * 2;   // x[480] and the two groups' buffers share this space (576 doubles)
 constexpr int kG8SLen = 130;
+constexpr int kG8MelMax = (kG8BlockDoubles - 480) / 2;   // mel coefficients whose exp() fits behind the waveform (48)
 
 struct G8WarpSmem {
     double xb[2][kG8BlockDoubles];                    // per block: waveform (480 doubles) / transposition buffers
@@ -130,7 +131,22 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
         // magnitudes of spectral frame k-1+frm at bins 0..128, and the initial waveform
         {
             const double* lm = logmel + (frame - 1 + frm) * n_mels;
-            for (int b = l8; b < kBins; b += 8) ws.S[blk][frm][b] = mel_magnitude(lm, tab.inv_idx, tab.inv_w, b);
+            if (n_mels <= kG8MelMax) {
+                // exp() once per mel coefficient (40 per frame) instead of once per inverse-mel tap (258 per frame): the values
+                // sit in the tail of the block's buffer, which the 480-sample waveform does not use
+                double* em = x + kBlk + frm * kG8MelMax;
+                for (int m = l8; m < n_mels; m += 8) em[m] = exp(lm[m]);
+                __syncwarp();
+                for (int b = l8; b < kBins; b += 8) {
+                    const double w0 = tab.inv_w[b * 2], w1 = tab.inv_w[b * 2 + 1];
+                    double v = 0.0;
+                    if (w0 != 0.0) v = em[tab.inv_idx[b * 2]] * w0;
+                    if (w1 != 0.0) v = fma(em[tab.inv_idx[b * 2 + 1]], w1, v);
+                    ws.S[blk][frm][b] = isfinite(v) ? v : 0.0;              // MelFilterBank.makeNormal
+                }
+            } else {
+                for (int b = l8; b < kBins; b += 8) ws.S[blk][frm][b] = mel_magnitude(lm, tab.inv_idx, tab.inv_w, b);
+            }
             const int l16 = lane & 15;
             for (int i = l16; i < kBlk; i += 16)
                 x[i] = noise ? noise[frame * kBlk + i] : uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)i);
