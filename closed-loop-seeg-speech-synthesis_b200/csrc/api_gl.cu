@@ -101,6 +101,7 @@ int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len,
     for (int k = 0; k < kBins; ++k) tf[k] = cplx{cos(2.0 * pi * k / kFft), -sin(2.0 * pi * k / kFft)};
     // exact values at the quadrant points keep the DC / Nyquist algebra free of 1e-17 leakage
     tf[0] = cplx{1, 0}; tf[kFft / 4] = cplx{0, -1}; tf[kFft / 2] = cplx{-1, 0};
+    for (int k = 1; k < kFft / 4; ++k) tf[kFft / 2 - k] = cplx{-tf[k].x, tf[k].y};      // w[128 - k] = -conj(w[k]) to the bit (gl_blocks8.cuh relies on it)
     // W128^(l k1) for the register-FFT kernel (gl_blocks8.cuh): [k1][l] with rows padded to 9 entries
     std::vector<cplx> tt(16 * 9, cplx{0, 0});
     for (int k1 = 0; k1 < 16; ++k1)

@@ -90,6 +90,12 @@ __device__ __forceinline__ void g8_pair(cplx& A, cplx& B, cplx w, cplx w2, doubl
     B = cplx{fma(w2.y, -df, sm), w2.x * df};
 }
 
+// magnitudes are stored as partner pairs (S[p], S[128 - p]) at index p <= 64, so the phase step fetches both with one load
+__device__ __forceinline__ void g8_store_mag(double* S, int bin, double v) {
+    if (bin <= kHalf / 2) S[2 * bin] = v;
+    if (bin >= kHalf / 2) S[2 * (kHalf - bin) + 1] = v;
+}
+
 __device__ __forceinline__ cplx csel(bool c, cplx a, cplx b) { return {c ? a.x : b.x, c ? a.y : b.y}; }
 
 template <int WARPS, int MINB>
@@ -142,10 +148,11 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                     double v = 0.0;
                     if (w0 != 0.0) v = em[tab.inv_idx[b * 2]] * w0;
                     if (w1 != 0.0) v = fma(em[tab.inv_idx[b * 2 + 1]], w1, v);
-                    ws.S[blk][frm][b] = isfinite(v) ? v : 0.0;              // MelFilterBank.makeNormal
+                    v = isfinite(v) ? v : 0.0;                              // MelFilterBank.makeNormal
+                    g8_store_mag(ws.S[blk][frm], b, v);
                 }
             } else {
-                for (int b = l8; b < kBins; b += 8) ws.S[blk][frm][b] = mel_magnitude(lm, tab.inv_idx, tab.inv_w, b);
+                for (int b = l8; b < kBins; b += 8) g8_store_mag(ws.S[blk][frm], b, mel_magnitude(lm, tab.inv_idx, tab.inv_w, b));
             }
             const int l16 = lane & 15;
             for (int i = l16; i < kBlk; i += 16)
@@ -195,7 +202,11 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
             for (int i = 0; i < 8; ++i) {
                 const int kk = lane0 ? (i < 4 ? 8 + 16 * i : 16 * (i - 3)) : l8 + 16 * i;
                 cplx B = V[7 - i];
-                g8_pair(U[i], B, s_tw_full[kk], s_tw_full[kHalf - kk], Sg[kk], Sg[kHalf - kk]);
+                // partner twiddle w[128 - kk] = -conj(w[kk]) (the host table is built with that symmetry)
+                const cplx w = s_tw_full[kk];
+                const bool upper = !lane0 && i >= 4;                         // kk > 64: the pair sits at 128 - kk, swapped
+                const double2 sp = *reinterpret_cast<const double2*>(Sg + 2 * (upper ? kHalf - kk : kk));
+                g8_pair(U[i], B, w, cplx{0.0 - w.x, w.y}, upper ? sp.y : sp.x, upper ? sp.x : sp.y);      // 0.0 - x: no -0.0 at the quadrant point
                 if (i != 7) V[7 - i] = B;                                    // pair 7 of lane 0 is the self-pair (64, 64): V[0] unused
                 else V[0] = lane0 ? V[0] : B;
             }
@@ -204,7 +215,7 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                 // DC and Nyquist are real with imag = +0.0 in numpy: angle is 0 or pi
                 const double xdc = dc.x + dc.y, xny = dc.x - dc.y;
                 const double zdc = Sg[0] * ((xdc < 0.0 || (xdc == 0.0 && signbit(xdc))) ? exp_pi : 1.0);
-                const double zny = Sg[kHalf] * ((xny < 0.0 || (xny == 0.0 && signbit(xny))) ? exp_pi : 1.0);
+                const double zny = Sg[1] * ((xny < 0.0 || (xny == 0.0 && signbit(xny))) ? exp_pi : 1.0);
                 zdcny = cplx{zdc + zny, -(zdc - zny)};
             }
             // back to rows (natural k2 order for the next transform)
