@@ -11,29 +11,49 @@ from . import _lib
 TOL = 1e-4                      # sklearn LinearDiscriminantAnalysis default
 
 
+def _dev(a, dtype='float64'):
+    """numpy -> contiguous host array; torch CUDA tensor -> contiguous tensor of the wanted dtype (stays on the device)."""
+    if _lib._is_torch(a):
+        import torch
+        return a.to(getattr(torch, dtype)).contiguous()
+    return np.ascontiguousarray(a, dtype=getattr(np, dtype))
+
+
+def _empty_like_kind(ref, shape, dtype='float64'):
+    if _lib._is_torch(ref):
+        import torch
+        return torch.empty(shape, dtype=getattr(torch, dtype), device=ref.device)
+    return np.empty(shape, dtype=getattr(np, dtype))
+
+
+def _to_host(a):
+    return a.cpu().numpy() if _lib._is_torch(a) else a
+
+
 # ---- quantisation (train.py:78-93) ----------------------------------------------------------------------
 def quantization(y_train, nb_intervals=9):
+    """y_train (N x bins), numpy or torch-CUDA.  medians / borders are small host arrays; the labels stay where y lives."""
     from local.quantization import compute_borders_logistic
-    y = np.ascontiguousarray(y_train, dtype=np.float64)
+    y = _dev(y_train)
     _lib.ensure_init()
-    mn = np.empty(y.shape[1]); mx = np.empty(y.shape[1])
-    _lib.check(_lib.lib().sgs_col_minmax(_lib.ptr(y), y.shape[0], y.shape[1], _lib.ptr(mn), _lib.ptr(mx), None))
-    medians, borders = compute_borders_logistic(np.vstack([mn, mx]), nb_intervals)      # only min/max enter the formula
+    mn, mx = _empty_like_kind(y, (y.shape[1],)), _empty_like_kind(y, (y.shape[1],))
+    st = _lib.current_stream(y)
+    _lib.check(_lib.lib().sgs_col_minmax(_lib.ptr(y), y.shape[0], y.shape[1], _lib.ptr(mn), _lib.ptr(mx), st))
+    medians, borders = compute_borders_logistic(np.vstack([_to_host(mn), _to_host(mx)]), nb_intervals)   # only min/max enter the formula
     borders = np.ascontiguousarray(borders)
-    q = np.empty_like(y)
-    _lib.check(_lib.lib().sgs_quantize(_lib.ptr(y), y.shape[0], y.shape[1], _lib.ptr(borders), nb_intervals, _lib.ptr(q), None))
+    q = _empty_like_kind(y, tuple(y.shape))
+    _lib.check(_lib.lib().sgs_quantize(_lib.ptr(y), y.shape[0], y.shape[1], _lib.ptr(borders), nb_intervals, _lib.ptr(q), st))
     return medians, borders, q
 
 
 # ---- feature selection (train.py:96-109) ------------------------------------------------------------------
 def spearman(x_train, y_train):
-    x = np.ascontiguousarray(x_train, dtype=np.float64)
-    y = np.ascontiguousarray(y_train, dtype=np.float64)
+    x, y = _dev(x_train), _dev(y_train)
     n = min(len(x), len(y))
     _lib.ensure_init()
-    rho = np.empty(x.shape[1]); colsum = np.empty(x.shape[1])
+    rho, colsum = np.empty(x.shape[1]), np.empty(x.shape[1])
     _lib.check(_lib.lib().sgs_spearman(_lib.ptr(x), n, x.shape[1], x.shape[1], _lib.ptr(y), y.shape[1], _lib.ptr(rho),
-                                       _lib.ptr(colsum), None))
+                                       _lib.ptr(colsum), _lib.current_stream(x)))
     return rho, colsum
 
 
@@ -48,25 +68,25 @@ def feature_selection(x_train, y_train, nb_feats=150):
 
 # ---- LDA fit from sufficient statistics (train.py:112-118, closed form R5) --------------------------------
 def lda_stats(x_train, select, labels, n_classes=9, xbar=None):
-    """x_train (N x width) full stacked features, select -> model columns, labels (N x bins)."""
-    x = np.ascontiguousarray(x_train, dtype=np.float64)
-    lab = np.ascontiguousarray(labels, dtype=np.float64)
+    """x_train (N x width) full stacked features, select -> model columns, labels (N x bins); numpy or torch-CUDA.
+    The statistics come back as (small) host arrays."""
+    x, lab = _dev(x_train), _dev(labels)
     sel = np.ascontiguousarray(select, dtype=np.int32)
     n, nf, nb = len(x), len(sel), lab.shape[1]
     _lib.ensure_init()
     out_xbar = np.empty(nf); G = np.empty((nf, nf)); sums = np.empty((nb, n_classes, nf)); counts = np.empty((nb, n_classes))
     xin = None if xbar is None else np.ascontiguousarray(xbar, dtype=np.float64)
     _lib.check(_lib.lib().sgs_lda_stats(_lib.ptr(x), n, x.shape[1], _lib.ptr(sel), nf, _lib.ptr(lab), nb, n_classes, _lib.ptr(xin),
-                                        _lib.ptr(out_xbar), _lib.ptr(G), _lib.ptr(sums), _lib.ptr(counts), None))
+                                        _lib.ptr(out_xbar), _lib.ptr(G), _lib.ptr(sums), _lib.ptr(counts), _lib.current_stream(x)))
     return dict(n=float(n), xbar=out_xbar, G=G, sums=sums, counts=counts)
 
 
 def col_means(x_train, select):
-    x = np.ascontiguousarray(x_train, dtype=np.float64)
+    x = _dev(x_train)
     sel = np.ascontiguousarray(select, dtype=np.int32)
     _lib.ensure_init()
     out = np.empty(len(sel))
-    _lib.check(_lib.lib().sgs_col_means(_lib.ptr(x), len(x), x.shape[1], _lib.ptr(sel), len(sel), _lib.ptr(out), None))
+    _lib.check(_lib.lib().sgs_col_means(_lib.ptr(x), len(x), x.shape[1], _lib.ptr(sel), len(sel), _lib.ptr(out), _lib.current_stream(x)))
     return out
 
 

@@ -26,8 +26,13 @@ logger = logging.getLogger('train.py')
 def quantization(y_train, nb_intervals=8):
     """Quantize the logMel spectrogram."""
     medians, borders, q_spectrogram = training.quantization(y_train, nb_intervals)
-    for i in range(q_spectrogram.shape[1]):
-        diff = np.setdiff1d(np.arange(0, nb_intervals), q_spectrogram[:, i])
+    if isinstance(q_spectrogram, np.ndarray):
+        present = np.stack([(q_spectrogram == k).any(axis=0) for k in range(nb_intervals)])
+    else:                                                     # device-resident labels: nine small reductions, no download
+        import torch
+        present = torch.stack([(q_spectrogram == k).any(dim=0) for k in range(nb_intervals)]).cpu().numpy()
+    for i in range(present.shape[1]):
+        diff = np.nonzero(~present[:, i])[0]
         if diff.size > 0:
             logger.info('Spec_bin "{}" misses samples for interval index/indices "{}"'.format(i, str(diff)))
     return medians, borders, q_spectrogram
@@ -62,31 +67,44 @@ def compute_features(eeg, sfreq_eeg, audio, audio_sr):
 
 
 def train(eeg, audio, sfreq_eeg, sfreq_audio, bad_channels, nb_mel_bins=40):
+    """Host arrays in, host arrays + fitted estimators out, as in the reference - but the recording and the audio are moved to
+    the device once and every stage in between (channel selection, features, decimation, log-mel target, quantisation,
+    Spearman ranking, column selection, LDA statistics) works on device-resident tensors."""
+    import torch
+    from sgs import _lib
+    _lib.ensure_init()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    eeg = np.asarray(eeg)
+    if eeg.dtype not in (np.float32, np.float64):
+        eeg = eeg.astype(np.float64)
+    eeg_d = torch.from_numpy(eeg).to(dev)
+    audio_d = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float64)).to(dev)
     if len(bad_channels) > 0:
         logger.info('EEG original shape: {} x {}'.format(*eeg.shape))
         mask = np.ones(eeg.shape[1], bool)
         mask[bad_channels] = False
-        eeg = eeg[:, mask]
-        logger.info('EEG truncated shape: {} x {}'.format(*eeg.shape))
+        eeg_d = eeg_d[:, torch.from_numpy(mask).to(dev)].contiguous()
+        logger.info('EEG truncated shape: {} x {}'.format(*eeg_d.shape))
     else:
         logger.info('No bad channels specified.')
 
-    x_train, y_train = compute_features(eeg, sfreq_eeg, audio, sfreq_audio)
+    x_train, y_train = compute_features(eeg_d, sfreq_eeg, audio_d, sfreq_audio)
+    del eeg_d, audio_d
     y_train = y_train[20:-4]          # align the audio frames with the 20-frame context / 50 ms window of the features
 
     medians, borders, q_spectrogram = quantization(y_train, nb_intervals=9)
     select = feature_selection(x_train, y_train)
-    x_train = x_train[:, select]
+    x_train = x_train[:, torch.from_numpy(np.ascontiguousarray(select, dtype=np.int64)).to(dev)].contiguous()
 
     estimators = [None for _ in range(nb_mel_bins)]
     y_train = q_spectrogram
-    logger.info('x_train: ' + str(x_train.shape))
-    logger.info('y_train: ' + str(y_train.shape))
+    logger.info('x_train: ' + str(tuple(x_train.shape)))
+    logger.info('y_train: ' + str(tuple(y_train.shape)))
     minimum = min(len(x_train), len(y_train))
     x_train = x_train[0:minimum, :]
     y_train = y_train[0:minimum, :]
     train_estimators(estimators=estimators, x_train=x_train, y_train=y_train)
-    return x_train, y_train, medians, estimators, select
+    return x_train.cpu().numpy(), y_train.cpu().numpy(), medians, estimators, select
 
 
 def store_training_to_file(config, x_train, y_train, medians, estimators, bad_channels, select):
