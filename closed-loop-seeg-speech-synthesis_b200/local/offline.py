@@ -2,6 +2,7 @@
 
     herff2016_b          local/offline.py:12-128   high-gamma log-power features (+ temporal stacking)
     griffin_lim          local/offline.py:131-192  batch Griffin-Lim (800-point frames, complex phase)
+    pearson_correlation  local/offline.py:195-216  evaluation metric: per-bin Pearson r between two spectrograms
     compute_spectrogram  local/offline.py:219-241  audio -> 40-bin log-mel target
 
 Arrays go in and come out as numpy (host) or as torch CUDA tensors (resident); nothing is computed on the CPU
@@ -45,3 +46,20 @@ def griffin_lim(spectrogram, win_length=0.05, hop_size=0.01, num_iterations=8, n
 def compute_spectrogram(audio, sr=16000, window_length=0.05, window_shift=0.01, mel_bins=40):
     from sgs.spectrogram import log_mel_spectrogram
     return log_mel_spectrogram(audio, sr, window_length, window_shift, mel_bins)
+
+
+def pearson_correlation(spectrogram_1, spectrogram_2, return_means=False):
+    """Mean and standard deviation over the mel bins of the per-bin Pearson correlation between two spectrograms
+    (frames x bins); with return_means also the list of per-bin values.  Evaluation metric, O(frames x bins)."""
+    if isinstance(spectrogram_1, str):
+        spectrogram_1 = np.load(spectrogram_1)
+    if isinstance(spectrogram_2, str):
+        spectrogram_2 = np.load(spectrogram_2)
+    a, b = np.asarray(spectrogram_1, dtype=np.float64), np.asarray(spectrogram_2, dtype=np.float64)
+    assert a.shape == b.shape, 'Shapes of spectrograms do not match.'
+    a = a - a.mean(axis=0)
+    b = b - b.mean(axis=0)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        rs = list((a * b).sum(axis=0) / np.sqrt((a * a).sum(axis=0) * (b * b).sum(axis=0)))
+    mean, std = np.mean(rs), np.std(rs)
+    return (mean, std, rs) if return_means else (mean, std)
