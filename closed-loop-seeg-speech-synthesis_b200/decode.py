@@ -147,8 +147,8 @@ def _reference_noise(n_frames, block=480, first=1):
     rs = np.random.RandomState()
     rs.set_state(np.random.get_state())
     noise = np.zeros((n_frames, block))
-    for k in range(first, n_frames):
-        noise[k] = rs.rand(block)
+    if n_frames > first:
+        noise[first:] = rs.rand(n_frames - first, block)      # one call = the same MT19937 stream as a rand(480) per frame
     return noise
 
 
