@@ -34,7 +34,7 @@ constexpr int kBBytes = (kTcK / 4) * kLBO;              // one 128 x 160 tf32 op
 constexpr int kHalfStage = (kTcChunk / 4) * kLBO;       // hi (or lo) part of one chunk: 8 192 B
 constexpr int kAStageBytes = 2 * kHalfStage;
 constexpr int kTileBytes = 2 * kBBytes;                 // packed A tile in HBM: hi matrix then lo matrix
-constexpr int kTcTail = 256 + kTcN * 8 + 16 * 8;        // barriers + bias + per-bin weight norms
+constexpr int kTcTail = 256 + kTcN * 8 + 16 * 8 + kTcN * 4 + 2 * 16 * 4;   // barriers + bias + per-bin weight norms + fp32 copies
 constexpr int kTcSmem = 2 * kBBytes + kTcStages * kAStageBytes + kTcTail;
 
 
@@ -185,41 +185,62 @@ k_lda_tc(const float* __restrict__ packed, const double* __restrict__ xnorm2, co
         }
     } else {
         // ===== epilogue (warps 0-3): thread = accumulator row, warp w owns TMEM lanes 32w.. =====
+        // Fully unrolled over the 126 score columns (bin = column / 9, class = column % 9 are compile-time), comparisons in fp32:
+        // the first version walked the columns with run-time bin / class counters in fp64 - 3650 instructions per thread and tile,
+        // branch_resolving the second largest stall, and with one epilogue warp per scheduler that was the kernel's critical path
+        // (tensor pipe 17 % busy).  The extra rounding of the fp32 bias add is part of the tie threshold below.
+        float* s_biasf = reinterpret_cast<float*>(s_wnorm + 16);            // [128] bias' as float
+        float* s_tol = s_biasf + kTcN;                                      // [16]  per-bin 2^-22 max|bias'| (rounding of the bias)
+        float* s_wnf = s_tol + 16;                                          // [16]  per-bin weight norm, rounded up
+        for (int i = tid; i < kTcN; i += 128) s_biasf[i] = (float)s_bias[i];
+        if (tid < 16) {
+            double bm = 0.0;
+            for (int k = 0; k < kTcClasses; ++k) {
+                const double bv = tid * kTcClasses + k < kTcN ? s_bias[tid * kTcClasses + k] : 0.0;
+                if (isfinite(bv)) bm = fmax(bm, fabs(bv));
+            }
+            s_tol[tid] = (float)(bm * 2.4e-7) * 1.0001f;
+            s_wnf[tid] = (float)s_wnorm[tid] * 1.0001f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");                      // epilogue warps only
         uint32_t t_local = 0;
         for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++t_local) {
             const uint32_t buf = t_local & 1;
             const int sess = tile / g.tiles_per_session;
             const int erow = (tile - sess * g.tiles_per_session) * kTcM + tid;
             const bool elive = erow < g.n_rows;
-            const double margin0 = 2.0 * g.eps * sqrt(xnorm2[(size_t)tile * kTcM + tid]);   // x |w|_2 of the bin bounds sum |x' w|
+            // x |w|_2 of the bin bounds sum |x' w|; rounded up when narrowed to float
+            const float margin0 = (float)(2.0 * g.eps * sqrt(xnorm2[(size_t)tile * kTcM + tid])) * 1.0001f;
+            double* lab_row = labels + ((long long)sess * g.n_rows + erow) * g.n_bins + bin0;
+            const double* cls_s = cls + slice * kTcN;
             mbar_wait(bar_acc_full + 8 * buf, (t_local >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             bool tie = false;
-            double best = -INFINITY, second = -INFINITY;
-            int best_k = 0, bin = 0, kk = 0;
-#pragma unroll 1
+            float best = -INFINITY, second = -INFINITY;
+            int best_k = 0;
+#pragma unroll
             for (int c0 = 0; c0 < kTcN; c0 += 32) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem + buf * kTcN + ((uint32_t)(warp * 32) << 16) + c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(tmem + buf * kTcN + ((uint32_t)(warp * 32) << 16) + c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    if (bin < nb) {
-                        const double sc = (double)__uint_as_float(v[j]) + s_bias[c0 + j];
-                        if (sc > best) { second = best; best = sc; best_k = kk; }
-                        else if (sc > second) second = sc;
-                        if (++kk == kTcClasses) {
-                            if (best - second < margin0 * s_wnorm[bin]) tie = true;
-                            if (elive) labels[((long long)sess * g.n_rows + erow) * g.n_bins + bin0 + bin] = cls[slice * kTcN + bin * kTcClasses + best_k];
-                            kk = 0; ++bin; best = -INFINITY; second = -INFINITY; best_k = 0;
+                    constexpr int kBinsPerSlice = kTcN / kTcClasses;        // 14
+                    const int col = c0 + j, bin = col / kTcClasses, kk = col - bin * kTcClasses;
+                    if (bin < kBinsPerSlice) {
+                        const float sc = __uint_as_float(v[j]) + s_biasf[col];
+                        const bool gt = sc > best;                          // strict: the first maximum wins, as numpy argmax
+                        second = gt ? best : fmaxf(second, sc);
+                        best_k = gt ? kk : best_k;
+                        best = gt ? sc : best;
+                        if (kk == kTcClasses - 1) {
+                            if (bin < nb) {
+                                // |fp32 score - exact| <= eps |x'| |w| (tensor-core split) + rounding of the bias and of the fp32 add
+                                const float fin2 = second > -INFINITY ? fabsf(second) : 0.0f;
+                                const float thr = fmaf(margin0, s_wnf[bin], s_tol[bin]) + 4.8e-7f * (fabsf(best) + fin2);
+                                if (best - second < thr) tie = true;
+                                if (elive) lab_row[bin] = cls_s[bin * kTcClasses + best_k];
+                            }
+                            best = -INFINITY; second = -INFINITY; best_k = 0;
                         }
                     }
                 }
