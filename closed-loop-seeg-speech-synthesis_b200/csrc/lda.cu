@@ -14,6 +14,7 @@
 // Layout: W is repacked on upload to [bin][feature][class] so that the 9 class weights of one (bin, feature)
 // are contiguous and warp-uniform.  Block = 4 warps x 32 frames (lane = frame); warp w scores bins w, w+4, ...
 #include <math.h>
+#include <algorithm>
 #include "kernels.cuh"
 
 namespace sgs {
@@ -34,15 +35,17 @@ k_lda_decode(const double* __restrict__ feat, const double* __restrict__ Wt /*[b
     double* xs = sm;                                   // [F][33]
     double* raw = sm + (size_t)g.n_features * 33;      // [n_bins][33]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // list mode (exact re-scoring of the frames the tensor-core pass flagged): a fixed grid strides over the list, whose
+    // length is only known on the device; otherwise one pass with vb = blockIdx.x
+    const int n_list = list ? *list_count : 0;
+    for (int vb = blockIdx.x; list ? vb * kLdaFrames < n_list : vb == (int)blockIdx.x; vb += gridDim.x) {
     int sess = blockIdx.y;
-    int row = blockIdx.x * kLdaFrames + lane;
+    int row = vb * kLdaFrames + lane;
     bool live = row < g.n_rows;
     if (list) {
-        // exact re-scoring of the frames the tensor-core pass flagged: frame id = session * n_rows + row
-        const int n = *list_count, i = blockIdx.x * kLdaFrames + lane;
-        if (blockIdx.x * kLdaFrames >= n) return;
-        live = i < n;
-        const int id = live ? list[i] : list[n - 1];
+        const int i = vb * kLdaFrames + lane;                   // frame id = session * n_rows + row
+        live = i < n_list;
+        const int id = live ? list[i] : list[n_list - 1];
         sess = id / g.n_rows;
         row = id - sess * g.n_rows;
     }
@@ -81,7 +84,7 @@ k_lda_decode(const double* __restrict__ feat, const double* __restrict__ Wt /*[b
         lv = lv < 0 ? 0 : (lv >= g.n_levels ? g.n_levels - 1 : lv);
         raw[b * 33 + lane] = medians[b * g.n_levels + lv];
     }
-    if (!spec) return;
+    if (spec) {
     __syncthreads();
     for (int b = warp; b < g.n_bins; b += kLdaWarps) {
         double v = raw[b * 33 + lane];
@@ -99,6 +102,9 @@ k_lda_decode(const double* __restrict__ feat, const double* __restrict__ Wt /*[b
             v = t;
         }
         if (live) spec[((long long)sess * g.n_rows + row) * g.n_bins + b] = v;
+    }
+    }
+    __syncthreads();                                            // xs / raw are reused by the next list block
     }
 }
 
@@ -188,7 +194,7 @@ int lda_run(const double* feat, const double* Wt, const double* bias, const doub
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lda_decode<kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     dim3 grid(ceil_div(g.n_rows, kLdaFrames), n_sessions);
-    if (list) grid = dim3(ceil_div(list_cap, kLdaFrames), 1);      // blocks past the list length exit at once
+    if (list) grid = dim3((int)std::min<long long>(ceil_div(list_cap, kLdaFrames), 148 * 8), 1);   // strides over the list
     { ProfScope ps(kProfLda, st); k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g, list, list_count); }
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
