@@ -14,9 +14,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -47,35 +45,42 @@ def random_model(rng, n_feat_total, n_bins=40, n_classes=9, n_sel=150):
     return (W, b, cls), select, synth.default_medians(n_bins, n_classes)
 
 
-def clocks_sampler(path):
-    q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    try:
-        return subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
-                                stdout=open(path, 'w'), stderr=subprocess.DEVNULL)
-    except OSError:
-        return None
+class ClockSampler:
+    """SM clock and clock-event (throttle) reasons of one GPU read through NVML - from the MAIN thread, right after the kernels of
+    the middle and of the last timed step have been enqueued (the device is then busy with them for ~94 ms, so the samples are
+    taken during the timed region).  NVML queries pause the device: the first ones of a process by 100-500 ms (paid during the
+    warm-up), later ones occasionally by tens of ms, hence only two.  Asynchronous sampling (an `nvidia-smi -lms` child at first, then a pynvml thread) made the first timed step
+    take 115-540 ms instead of 94 in most runs - a query that lands in the idle gap after the warm-up's synchronize - while
+    runs without any sampler never did (0 of 6 against 5 of 6, same box, same code)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
+    def __init__(self, device_index):
+        self.samples, self.max_mhz, self.ok = [], None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.ok = True
+        except Exception:
+            pass
 
-def clocks_summary(path, device_index, skip_lines=0):
-    sm, mx, reasons = [], 0.0, set()
-    try:
-        for i, line in enumerate(open(path)):
-            if i < skip_lines:
-                continue
-            f = [c.strip() for c in line.split(',')]
-            if len(f) < 9 or f[0] != str(device_index):
-                continue
-            try:
-                sm.append(float(f[1])); mx = max(mx, float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-    except OSError:
-        pass
-    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons)}
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append((float(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)), int(self._reasons(self._h))))
+        except Exception:
+            pass
+
+    def summary(self):
+        sm = [c for c, _ in self.samples]
+        reasons = sorted({name for _, bits in self.samples for bit, name in self.REASONS.items() if bits & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "NVML (pynvml) from the main thread while the kernels of the middle and of the last timed step run"}
 
 
 def bind_to_gpu_numa_node(local):
@@ -112,6 +117,8 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     _lib.ensure_init(local)
 
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get('SGS_BENCH_NO_CLOCKS') else None
+
     rng = np.random.default_rng(7)
     model, select, medians = random_model(rng, 5 * N_CH)
     decoder = dec_mod.OfflineDecoder(model, medians, select, SR, gl_norm=10, packet_size=64)
@@ -134,28 +141,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the clock sampler starts BEFORE the warm-up: nvidia-smi's own start-up (NVML initialisation, a few hundred ms) otherwise
-    # lands on the first timed step and stalls its launches; only samples taken inside the timed region are used
-    clk_path = os.path.join(tempfile.gettempdir(), 'sgs_clocks_%d.csv' % rank)
-    sampler = clocks_sampler(clk_path) if rank == 0 else None
+    _lib.profile_enable(True)              # per-kernel-class CUDA events also during the warm-up: their first creation is not free
     for _ in range(args.warmup):
         out = step()
+        if sampler is not None:
+            sampler.sample()               # the first NVML queries of a process are slow and pause the device: pay that here
     del out
     if sampler is not None:
-        torch.cuda.synchronize()
-        t_wait = time.time()
-        while (not os.path.exists(clk_path) or os.path.getsize(clk_path) == 0) and time.time() - t_wait < 5.0:
-            time.sleep(0.05)
-    _lib.profile_enable(True)
-    barrier()
-    clk_skip = sum(1 for _ in open(clk_path)) if sampler is not None and os.path.exists(clk_path) else 0
+        sampler.samples.clear()
+    # all housekeeping BEFORE the barrier, so that the device idles for the barrier only (a longer idle gap lets the clocks
+    # drop and the first timed step then pays the ramp: sporadic +30..100 ms on step 1)
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)              # resets the accumulators for the timed region
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
     ev0.record()
     for k in range(args.steps):
         out = step()
         marks[k].record()
+        if sampler is not None and k in (args.steps // 2, args.steps - 1):
+            sampler.sample()               # the device is still executing step k; two samples only: a query can pause the device
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -163,8 +170,6 @@ def run_ours(args):
     launches = _lib.launch_count() - n0
     prof = {k: _lib.profile_read(k) for k in ('iir_init', 'iir_state', 'iir_carry', 'iir_feat', 'lda_tc', 'lda', 'gl_blocks', 'gl_ola', 'lowpass')}
     _lib.profile_enable(False)
-    if sampler is not None:
-        sampler.terminate(); sampler.wait()
     spec, audio = out
     n_frames, n_audio = spec.shape[1], audio.shape[1]
     del out, spec, audio
@@ -244,7 +249,7 @@ def run_ours(args):
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "ms_each_step": [round(v, 3) for v in step_ms],
             "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
-            "clocks": clocks_summary(clk_path, local, clk_skip),
+            "clocks": sampler.summary() if sampler is not None else None,
         }
         line["cpu_baseline"] = cpu_baseline_sample()
         line["latency"] = latency_leg() if world == 1 and not args.no_latency else None
