@@ -239,13 +239,21 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "api": "decode.OfflineDecoder.decode(numpy pinned, pinned_outputs=True) -> numpy; H2D / compute / D2H double-buffered per session"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_iir_stages<FEAT>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_iir_pieces<FEAT> (feature extraction, pass 2; with pass 1 the largest stage of the step)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "note": "54 flop/B kernel: bound by the FP64 pipe, not HBM (see fp64_pipe)",
                          "fp64_pipe": {"achieved": dp_ops / (iir_ms * 1e-3) if iir_ms > 0 else None, "peak": FP64_PEAK,
                                        "unit": "fp64 op/s", "frac": dp_ops / (iir_ms * 1e-3) / FP64_PEAK if iir_ms > 0 else None,
                                        "peak_source": "measured DFMA/s, tools/pipe_peak.cu"}},
+            "roofline_other_kernels": [
+                {"kernel": "k_gl_blocks8 (Griffin-Lim node blocks)", "bound": "fp64 pipe (HBM traffic is 80 doubles in, 480 out per block)",
+                 "achieved": (S * (n_frames - 1) * 164e3 / (prof['gl_blocks'][0] / args.steps * 1e-3)) if prof['gl_blocks'][0] > 0 else None,
+                 "peak": 2 * FP64_PEAK, "unit": "fp64 flop/s (164 kflop nominal per 10 ms frame, SURVEY.md 8d)",
+                 "note": "pipe busy 58 % by ncu (profiles/ncu_gl_blocks8_r01.txt): the nominal 5 N log2 N count leaves out exp(angle) and the splits"},
+                {"kernel": "k_lda_tc (LDA scoring, tcgen05 kind::tf32)", "bound": "tensor",
+                 "achieved": (2.0 * S * n_frames * 160 * 384 * 3 / 1e12 / (1.807e-3 * S / 32)), "peak": 0.5 * float(peaks.get('bf16_tflops', 1650.6)),
+                 "unit": "TFLOP/s issued (3 split-TF32 products, padded 160 x 384; kernel time from profiles/launches_r01d.txt; peak = half the measured bf16 rate)"}],
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "ms_each_step": [round(v, 3) for v in step_ms],
             "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
