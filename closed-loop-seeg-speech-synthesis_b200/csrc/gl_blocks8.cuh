@@ -78,12 +78,12 @@ struct G8Tables {
 
 // one real-FFT bin pair (kk, 128 - kk): split, Z = S exp(angle X), inverse split (stored conjugated); identical
 // arithmetic to the shared-memory kernel
-__device__ __forceinline__ void g8_pair(cplx& A, cplx& B, cplx w, cplx w2, double s1, double s2) {
+__device__ __forceinline__ void g8_pair(const double* s_ea, cplx& A, cplx& B, cplx w, cplx w2, double s1, double s2) {
     const cplx d1 = cplx{A.x - B.x, A.y + B.y}, t1 = cmul(w, d1);
     const double re1 = 0.5 * (A.x + B.x) + 0.5 * t1.y, im1 = 0.5 * (A.y - B.y) - 0.5 * t1.x;
     const cplx d2 = cplx{B.x - A.x, B.y + A.y}, t2 = cmul(w2, d2);
     const double re2 = 0.5 * (B.x + A.x) + 0.5 * t2.y, im2 = 0.5 * (B.y - A.y) - 0.5 * t2.x;
-    const double2 ea = exp_angle_pair_call(im1, re1, im2, re2);
+    const double2 ea = exp_angle_pair_call(s_ea, im1, re1, im2, re2);
     const double z1 = s1 * ea.x, z2 = s2 * ea.y;
     const double sm = z1 + z2, df = z1 - z2;
     A = cplx{fma(w.y, df, sm), -(w.x * df)};
@@ -107,7 +107,9 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
     double* s_window = reinterpret_cast<double*>(smem_raw);                 // [256]
     cplx* s_tw_full = reinterpret_cast<cplx*>(s_window + kFft);             // [130]
     cplx* s_tw_t = s_tw_full + kG8SLen;                                     // [16 * 9]
-    G8WarpSmem* ws_all = reinterpret_cast<G8WarpSmem*>(s_tw_t + kG8BufCplx);
+    double* s_ea = reinterpret_cast<double*>(s_tw_t + kG8BufCplx);          // [72] constants of exp(angle)
+    G8WarpSmem* ws_all = reinterpret_cast<G8WarpSmem*>(s_ea + kEaTabLen);
+    exp_angle_load_table(s_ea);
     for (int i = threadIdx.x; i < kFft; i += blockDim.x) s_window[i] = tab.window[i];
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) s_tw_full[i] = tab.tw_full[i];
     for (int i = threadIdx.x; i < kG8BufCplx; i += blockDim.x) s_tw_t[i] = tab.tw_t[i];
@@ -122,7 +124,7 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
     cplx* buf = reinterpret_cast<cplx*>(ws.xb[blk]) + frm * kG8BufCplx;     // this group's transposition buffer (aliases x)
     const double* Sg = ws.S[blk][frm];
     const int per_sess = n_frames - first_frame;
-    const double exp_pi = exp_angle(0.0, -1.0);
+    const double exp_pi = kExpPi;                                           // exp(angle(-1 + 0j))
     const long long n_pairs = (n_items + 1) >> 1;
     constexpr double scale = 1.0 / kFft;
 
@@ -206,7 +208,7 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                 const cplx w = s_tw_full[kk];
                 const bool upper = !lane0 && i >= 4;                         // kk > 64: the pair sits at 128 - kk, swapped
                 const double2 sp = *reinterpret_cast<const double2*>(Sg + 2 * (upper ? kHalf - kk : kk));
-                g8_pair(U[i], B, w, cplx{0.0 - w.x, w.y}, upper ? sp.y : sp.x, upper ? sp.x : sp.y);      // 0.0 - x: no -0.0 at the quadrant point
+                g8_pair(s_ea, U[i], B, w, cplx{0.0 - w.x, w.y}, upper ? sp.y : sp.x, upper ? sp.x : sp.y);      // 0.0 - x: no -0.0 at the quadrant point
                 if (i != 7) V[7 - i] = B;                                    // pair 7 of lane 0 is the self-pair (64, 64): V[0] unused
                 else V[0] = lane0 ? V[0] : B;
             }

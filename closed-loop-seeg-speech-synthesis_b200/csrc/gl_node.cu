@@ -45,18 +45,12 @@ __device__ __noinline__ double mel_magnitude(const double* lm, const int* inv_id
 }
 
 // out-of-line copy of the pair evaluation: one body in the instruction cache, called 4 times per iteration
-__device__ __noinline__ double2 exp_angle_pair_call(double im1, double re1, double im2, double re2) {
+__device__ __noinline__ double2 exp_angle_pair_call(const double* s_tab, double im1, double re1, double im2, double re2) {
     double a, b;
-    exp_angle_pair(im1, re1, im2, re2, a, b);
+    exp_angle_pair(s_tab, im1, re1, im2, re2, a, b);
     return make_double2(a, b);
 }
 
-// exp(np.angle(re + 1j*im)) for one value (block set-up only; the iteration uses exp_angle_pair, exp_angle.cuh)
-__device__ __forceinline__ double exp_angle(double im, double re) {
-    double a, b;
-    exp_angle_pair(im, re, im, re, a, b);
-    return a;
-}
 
 }  // namespace sgs
 #include "gl_blocks8.cuh"
@@ -286,8 +280,15 @@ __global__ void k_lp_carry_par(const double* __restrict__ e, double* __restrict_
 
 // test hook: the kernel's exp(angle()) on arbitrary inputs (tests/test_gpu_decode.py checks it against numpy and mpmath)
 __global__ void k_exp_angle(const double* __restrict__ im, const double* __restrict__ re, long long n, double* __restrict__ out) {
+    __shared__ double s_tab[kEaTabLen];
+    exp_angle_load_table(s_tab);
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = exp_angle(im[i], re[i]);
+    if (i < n) {
+        double a, b;
+        exp_angle_pair(s_tab, im[i], re[i], im[i], re[i], a, b);
+        out[i] = a;
+    }
 }
 
 int exp_angle_run(const double* im, const double* re, long long n, double* out, cudaStream_t st) {
@@ -309,7 +310,7 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
     ProfScope ps(kProfGlBlocks, st);
     // 8 warps x 2 CTAs per SM: 128 registers per thread and 113 KB of shared memory per CTA (16 resident warps = 32 blocks)
     constexpr int W = 8;
-    const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kG8SLen + kG8BufCplx) + sizeof(G8WarpSmem) * W;
+    const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kG8SLen + kG8BufCplx) + sizeof(double) * kEaTabLen + sizeof(G8WarpSmem) * W;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_gl_blocks8<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     const long long n_pairs = (n_items + 1) / 2, want = (n_pairs + W - 1) / W;
