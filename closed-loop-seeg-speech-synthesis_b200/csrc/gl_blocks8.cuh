@@ -91,7 +91,9 @@ __device__ __forceinline__ void g8_pair(const double* s_ea, cplx& A, cplx& B, cp
 }
 
 // magnitudes are stored as partner pairs (S[p], S[128 - p]) at index p <= 64, so the phase step fetches both with one load
+// and carry the inverse transform's 1/256 (a power of two: scaling the magnitudes instead of the 256 output samples changes no bit)
 __device__ __forceinline__ void g8_store_mag(double* S, int bin, double v) {
+    v *= 1.0 / kFft;
     if (bin <= kHalf / 2) S[2 * bin] = v;
     if (bin >= kHalf / 2) S[2 * (kHalf - bin) + 1] = v;
 }
@@ -126,7 +128,6 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
     const int per_sess = n_frames - first_frame;
     const double exp_pi = kExpPi;                                           // exp(angle(-1 + 0j))
     const long long n_pairs = (n_items + 1) >> 1;
-    constexpr double scale = 1.0 / kFft;
 
     for (long long pr = (long long)blockIdx.x * WARPS + warp; pr < n_pairs; pr += (long long)gridDim.x * WARPS) {
         long long item = 2 * pr + blk;
@@ -252,7 +253,7 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                 for (int m = 0; m < 16; ++m) {
                     const int n = l8 + 8 * m;
                     const double2 wv = *reinterpret_cast<const double2*>(s_window + 2 * n);
-                    *reinterpret_cast<double2*>(x + 2 * n) = make_double2((v[pos16(m)].x * scale) * wv.x, (-v[pos16(m)].y * scale) * wv.y);
+                    *reinterpret_cast<double2*>(x + 2 * n) = make_double2(v[pos16(m)].x * wv.x, -v[pos16(m)].y * wv.y);
                 }
             }
             __syncwarp();
@@ -261,7 +262,7 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                 for (int m = 0; m < 16; ++m) {                               // frame 0 first: the overlap is (0 + r0) + r1
                     const int n = l8 + 8 * m, p = 2 * n;
                     const double2 wv = *reinterpret_cast<const double2*>(s_window + p);
-                    const double r0 = (v[pos16(m)].x * scale) * wv.x, r1 = (-v[pos16(m)].y * scale) * wv.y;
+                    const double r0 = v[pos16(m)].x * wv.x, r1 = -v[pos16(m)].y * wv.y;
                     double2 cur = *reinterpret_cast<const double2*>(x + kHop + p);
                     cur.x = (p < kFft - kHop) ? cur.x + r0 : r0;
                     cur.y = (p + 1 < kFft - kHop) ? cur.y + r1 : r1;
