@@ -9,7 +9,13 @@
                                 throughput possible.  Set streaming=True to run the node graph instead.
     decode_sessions             many equally long sessions at once, device-resident (the throughput path).
     session_shard               which sessions this rank decodes when one process per GPU shares a job (no collective).
+    load_params / load_seeg / store_decoding_to_file
+                                the artefacts either side of a decoding run (decode.py:186-219, 299-313): params.h5, the
+                                sEEG recording, audio.wav, spectrogram.npy, sEEG.hdf.  HDF5 goes through h5py when it is
+                                importable; without it the same datasets are read from / written to .npz files of the
+                                same stem (what train.store_training_to_file writes in that case).
 """
+import os
 import logging
 import pickle
 
@@ -196,3 +202,48 @@ def setup_decoder(eeg_sender, sfreq, estimators_serialized, medians_array, bad_c
         # loudspeaker sinks (JACK / PortAudio) are sound-hardware I/O and out of scope
         logger.info('No soundcard sink attached: audio is available from the returned Audio receiver.')
     return rec_seeg, rec_spec, rec_audio
+
+
+def _read_datasets(path, names):
+    """Datasets `names` of an HDF5 file, or of the .npz of the same stem when h5py is absent or the .npz is what exists."""
+    stem = os.path.splitext(path)[0]
+    if os.path.exists(path):
+        try:
+            import h5py
+        except ImportError:
+            raise ImportError('{} is an HDF5 file and h5py is not importable; store the datasets as {}.npz'.format(path, stem))
+        with h5py.File(path, 'r') as hf:
+            return {k: hf[k][...] for k in names}
+    with np.load(stem + '.npz') as z:
+        return {k: z[k] for k in names}
+
+
+def load_params(session_dir):
+    """(pickled estimators, medians_array, bad_channels, select) of a training session (decode.py:299-306)."""
+    d = _read_datasets(os.path.join(session_dir, 'params.h5'), ('medians_array', 'bad_channels', 'estimators', 'select'))
+    return d['estimators'].tobytes(), d['medians_array'], d['bad_channels'], d['select']
+
+
+def load_seeg(seeg_file):
+    """(eeg, sfreq) of a stored recording (decode.py:309-313)."""
+    d = _read_datasets(seeg_file, ('sEEG', 'sEEG_sr'))
+    return d['sEEG'], int(np.asarray(d['sEEG_sr']).reshape((1,))[0])
+
+
+def store_decoding_to_file(run_dir, spectrogram, output_audio, received_sEEG, sfreq, config=None):
+    """audio.wav (16 kHz int16), sEEG.hdf, spectrogram.npy and decode.ini in run_dir (decode.py:186-219; the plot is
+    out of scope).  run_dir is an argument here - the reference reads a module global set by its __main__."""
+    from scipy.io.wavfile import write as wavwrite
+    wavwrite(os.path.join(run_dir, 'audio.wav'), 16000, np.asarray(output_audio))
+    try:
+        import h5py
+        with h5py.File(os.path.join(run_dir, 'sEEG.hdf'), 'w') as hf:
+            hf.create_dataset('sEEG', data=received_sEEG)
+            hf.create_dataset('sEEG_sr', data=sfreq, dtype=np.int32)
+    except ImportError:
+        np.savez(os.path.join(run_dir, 'sEEG.npz'), sEEG=received_sEEG, sEEG_sr=np.int32(sfreq))
+    np.save(os.path.join(run_dir, 'spectrogram.npy'), spectrogram)
+    if config is not None:
+        with open(os.path.join(run_dir, 'decode.ini'), 'w') as configfile:
+            config.write(configfile)
+    logger.info('Decoding artefacts written to {}'.format(run_dir))

@@ -1,4 +1,6 @@
 """Host-side tables and runtime on CPU: window schedules, mel tables, scan planning, the Node callback runtime."""
+import os
+
 import numpy as np
 import pytest
 
@@ -185,3 +187,35 @@ def test_fused_chain_is_found_only_for_the_reference_wiring():
     LDASynthesis.LDASynthesis(blob, select=np.arange(4))(f3)
     LDASynthesis.LDASynthesis(blob, select=np.arange(4))(f3)
     assert chain.find_chain(f3) is None
+
+
+def test_artefacts_round_trip(tmp_path):
+    """params / recording / decoding artefacts either side of a run (train.py:171-205, decode.py:186-219, 299-313): what
+    train.store_training_to_file writes is what decode.load_params reads, and the decoding outputs come back bit-exact."""
+    import configparser
+    import pickle
+    from scipy.io.wavfile import read as wavread
+    import decode
+    import train
+    cfg = configparser.ConfigParser()
+    cfg['General'] = {'storage_dir': str(tmp_path), 'session': 's1'}
+    os.makedirs(tmp_path / 's1')
+    rng = np.random.default_rng(0)
+    medians, select, bad = rng.normal(size=(40, 9)), rng.permutation(640)[:150], np.array([3, 17])
+    estimators = [{'coef_': rng.normal(size=(9, 150))} for _ in range(3)]
+    train.store_training_to_file(cfg, rng.normal(size=(50, 150)), rng.normal(size=(50, 40)), medians, estimators, bad, select)
+    blob, m2, b2, s2 = decode.load_params(str(tmp_path / 's1'))
+    assert np.array_equal(m2, medians) and np.array_equal(b2, bad) and np.array_equal(s2, select)
+    back = pickle.loads(blob)
+    assert all(np.array_equal(a['coef_'], b['coef_']) for a, b in zip(back, estimators))
+    assert (tmp_path / 's1' / 'LDAs.pkl').exists() and (tmp_path / 's1' / 'train.ini').exists()
+
+    spec, audio = rng.normal(size=(30, 40)), rng.integers(-32768, 32767, 4800).astype(np.int16)
+    seeg = rng.normal(size=(614, 8)).astype(np.float32)
+    decode.store_decoding_to_file(str(tmp_path), spec, audio, seeg, 2048, config=cfg)
+    sr, a2 = wavread(str(tmp_path / 'audio.wav'))
+    assert sr == 16000 and a2.dtype == np.int16 and np.array_equal(a2, audio)
+    assert np.array_equal(np.load(tmp_path / 'spectrogram.npy'), spec)
+    e2, sf = decode.load_seeg(str(tmp_path / 'sEEG.hdf'))
+    assert sf == 2048 and np.array_equal(e2, seeg)
+    assert (tmp_path / 'decode.ini').exists()
