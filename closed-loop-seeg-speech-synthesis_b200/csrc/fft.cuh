@@ -90,13 +90,15 @@ __device__ __forceinline__ void fft128(cplx* a, cplx* b, const cplx* tw, int lan
     stockham_stage<128, 2, 64, SIGN>(b, a, tw, lane);
 }
 
-// 400-point complex FFT (radices 4,4,5,5): result ends in `a`.
+// 400-point complex FFT (radices 5,5,4,4): result ends in `a`.  The odd radices go first: a stage writes with a lane
+// stride of its radix (NS = 1) or in runs of NS entries, and strides of 5 and 25 complex values (80 / 400 B) spread over
+// all banks where 4 and 16 (64 / 256 B) pile 16 lanes onto the same four.
 template <int SIGN>
 __device__ __forceinline__ void fft400(cplx* a, cplx* b, const cplx* tw, int lane) {
-    stockham_stage<400, 4, 1, SIGN>(a, b, tw, lane);
-    stockham_stage<400, 4, 4, SIGN>(b, a, tw, lane);
-    stockham_stage<400, 5, 16, SIGN>(a, b, tw, lane);
-    stockham_stage<400, 5, 80, SIGN>(b, a, tw, lane);
+    stockham_stage<400, 5, 1, SIGN>(a, b, tw, lane);
+    stockham_stage<400, 5, 5, SIGN>(b, a, tw, lane);
+    stockham_stage<400, 4, 25, SIGN>(a, b, tw, lane);
+    stockham_stage<400, 4, 100, SIGN>(b, a, tw, lane);
 }
 
 template <int M, int SIGN> struct HalfFFT;

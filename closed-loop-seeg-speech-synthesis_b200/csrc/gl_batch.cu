@@ -11,19 +11,37 @@
 // The reference also transforms 5x more STFT frames than it uses and the last 5 spectral frames never reach the
 // output; neither is reproduced as work, both are reproduced as results.
 //
-// One CTA per utterance, 8 warps, one frame per warp per round.  Frames are processed in ascending order, which
+// One CTA per utterance, 13 warps, one frame per warp per round.  Frames are processed in ascending order, which
 // makes the update in place: hop segment h of x is final once frame h is done, and no later frame of the same
-// iteration reads it.  The windowed inverse transforms of the last 13 frames sit in a shared-memory ring so each
-// output sample is summed over its (up to 5) contributing frames in the reference's accumulation order.
+// iteration reads it.  The windowed inverse transforms of the last 18 frames sit in a shared-memory ring so each
+// output sample is summed over its (up to 5) contributing frames in the reference's accumulation order; a frame's
+// ring slot is free until its own result lands there, so it doubles as the second buffer of the Stockham stages.
 #include <math.h>
 #include "kernels.cuh"
 
 namespace sgs {
 
-constexpr int kBW = 8;                  // warps per CTA
+constexpr int kBW = 13;                 // warps per CTA (195 frames reach the output at T = 200: 15 full rounds)
 constexpr int kN = 800, kM = 400, kHopB = 160, kBinsB = 401, kOverlap = 5;
-constexpr int kRingB = kBW + kOverlap;  // 13 slots
+constexpr int kRingB = kBW + kOverlap;  // 18 slots
 
+// X / |X| without sqrt and divisions: reciprocal square root seed and two Newton steps (<= 2 ulp);
+// 0 -> (1, 0) as angle(0) = 0.  |X|^2 outside [2^-900, 2^900] takes the plain route.
+__device__ __forceinline__ cplx unit_phase(cplx X) {
+    const double m2 = fma(X.x, X.x, X.y * X.y);
+    if (__builtin_expect(!(m2 > 0x1p-900 && m2 < 0x1p+900), 0)) {
+        const double mag = hypot(X.x, X.y);
+        if (mag > 0.0 && isfinite(mag)) return cplx{X.x / mag, X.y / mag};
+        return cplx{1.0, 0.0};
+    }
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(m2));
+    double h = 0.5 * r, e = fma(-m2 * r, h, 0.5);                           // 0.5 - m2 r^2 / 2
+    r = fma(r, e, r);
+    h = 0.5 * r; e = fma(-m2 * r, h, 0.5);
+    r = fma(r, e, r);
+    return cplx{X.x * r, X.y * r};
+}
 
 __global__ void __launch_bounds__(kBW * 32)
 k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restrict__ x /*[B][x_len] in: noise, out: waveform*/,
@@ -32,17 +50,16 @@ k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restr
     double* s_window = reinterpret_cast<double*>(smem_raw);                 // [800]
     cplx* s_tw_half = reinterpret_cast<cplx*>(s_window + kN);               // [400]
     cplx* s_tw_full = s_tw_half + kM;                                       // [401] (+1 pad)
-    double* s_ring = reinterpret_cast<double*>(s_tw_full + kBinsB + 1);     // [13][800]
-    cplx* s_work = reinterpret_cast<cplx*>(s_ring + kRingB * kN);           // per warp: a[400], b[400]
-    double* s_exp = reinterpret_cast<double*>(s_work + kBW * 2 * kM);       // per warp: exp(logmel) [n_mels <= 64]
+    double* s_ring = reinterpret_cast<double*>(s_tw_full + kBinsB + 1);     // [18][800]
+    cplx* s_work = reinterpret_cast<cplx*>(s_ring + kRingB * kN);           // per warp: a[400]
+    double* s_exp = reinterpret_cast<double*>(s_work + kBW * kM);           // per warp: exp(logmel) [n_mels <= 64]
     for (int i = threadIdx.x; i < kN; i += blockDim.x) s_window[i] = tab.window[i];
     for (int i = threadIdx.x; i < kM; i += blockDim.x) s_tw_half[i] = tab.tw_half[i];
     for (int i = threadIdx.x; i < kBinsB; i += blockDim.x) s_tw_full[i] = tab.tw_full[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    cplx* a = s_work + (size_t)warp * 2 * kM;
-    cplx* b = a + kM;
+    cplx* a = s_work + (size_t)warp * kM;
     double* ex = s_exp + warp * 64;
     double* xu = x + (long long)blockIdx.x * x_len;
     const double* lm_u = logmel + (long long)blockIdx.x * T * n_mels;
@@ -50,9 +67,11 @@ k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restr
     constexpr double scale = 1.0 / kN;
 
     for (int it = 0; it < iters; ++it) {
-        for (int g0 = 0; g0 < T; g0 += kBW) {                               // rounds of 8 frames, ascending
+        for (int g0 = 0; g0 < T; g0 += kBW) {                               // rounds of kBW frames, ascending
             const int n = g0 + warp;
             if (n < n_used) {
+                double* slot = s_ring + (size_t)(n % kRingB) * kN;
+                cplx* b = reinterpret_cast<cplx*>(slot);                    // scratch until the frame's result is stored
                 for (int m = lane; m < n_mels; m += 32) ex[m] = exp(lm_u[(long long)n * n_mels + m]);
                 const double* xin = xu + (long long)n * kHopB;
                 for (int i = lane; i < kM; i += 32)
@@ -83,9 +102,8 @@ k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restr
                         if (w0 != 0.0) S = ex[tab.inv_idx[bin * 2]] * w0;
                         if (w1 != 0.0) S = fma(ex[tab.inv_idx[bin * 2 + 1]], w1, S);
                         if (!isfinite(S)) S = 0.0;
-                        const double mag = sqrt(fma(X.x, X.x, X.y * X.y));
-                        if (mag > 0.0) return cplx{S * (X.x / mag), S * (X.y / mag)};
-                        return cplx{S, 0.0};                                // angle(0) = 0
+                        const cplx u = unit_phase(X);
+                        return cplx{S * u.x, S * u.y};
                     };
                     const cplx Zk = project(Xk, k), Zk2 = project(Xk2, k2);
                     // irfft ignores the imaginary parts of the DC and Nyquist bins
@@ -108,7 +126,6 @@ k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restr
                 }
                 __syncwarp();
                 fft400<+1>(a, b, s_tw_half, lane);
-                double* slot = s_ring + (size_t)(n % kRingB) * kN;
                 for (int i = lane; i < kM; i += 32) {
                     slot[2 * i] = (a[i].x * scale) * s_window[2 * i];
                     slot[2 * i + 1] = (a[i].y * scale) * s_window[2 * i + 1];
@@ -156,7 +173,7 @@ __global__ void k_scale_int16(const double* __restrict__ x, long long x_len, lon
 int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int n_utt, int T, int n_mels, int iters,
                  long long x_len, double* mx, short* pcm, cudaStream_t st) {
     const size_t smem = sizeof(double) * kN + sizeof(cplx) * (kM + kBinsB + 1) + sizeof(double) * kRingB * kN +
-                        sizeof(cplx) * kBW * 2 * kM + sizeof(double) * kBW * 64;
+                        sizeof(cplx) * kBW * kM + sizeof(double) * kBW * 64;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_gl_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     {
