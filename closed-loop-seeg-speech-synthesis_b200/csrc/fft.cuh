@@ -56,7 +56,10 @@ template <int SIGN> struct Butterfly<5, SIGN> {
 
 // One Stockham stage of an N-point transform: radix R, NS = product of the radices already applied.
 // tw[t] = exp(-2*pi*i*t/N), t < N.  Reads a, writes b.
-template <int N, int R, int NS, int SIGN>
+// STAGED: tw is this stage's own table, tw[(r - 1) * NS + k] = exp(-2*pi*i*r*k/(NS*R)), so that the lanes of a warp
+// (consecutive k) read consecutive entries; the shared N-entry table is read with strides of N/(NS*R) entries, which
+// for NS = 25, N = 400 puts up to 25 lanes on one bank group.
+template <int N, int R, int NS, int SIGN, bool STAGED = false>
 __device__ __forceinline__ void stockham_stage(const cplx* __restrict__ a, cplx* __restrict__ b,
                                                const cplx* __restrict__ tw, int lane) {
     constexpr int M = N / R;
@@ -68,7 +71,7 @@ __device__ __forceinline__ void stockham_stage(const cplx* __restrict__ a, cplx*
         if (NS > 1) {
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                cplx w = tw[r * k * (N / (NS * R))];
+                cplx w = STAGED ? tw[(r - 1) * NS + k] : tw[r * k * (N / (NS * R))];
                 if (SIGN > 0) w.y = -w.y;
                 v[r] = cmul(v[r], w);
             }
@@ -93,12 +96,25 @@ __device__ __forceinline__ void fft128(cplx* a, cplx* b, const cplx* tw, int lan
 // 400-point complex FFT (radices 5,5,4,4): result ends in `a`.  The odd radices go first: a stage writes with a lane
 // stride of its radix (NS = 1) or in runs of NS entries, and strides of 5 and 25 complex values (80 / 400 B) spread over
 // all banks where 4 and 16 (64 / 256 B) pile 16 lanes onto the same four.
+constexpr int kFft400TwLen = 4 * 5 + 3 * 25 + 3 * 100;                     // per-stage twiddle tables of fft400 (395 entries)
+
+// builds the per-stage tables from tw400[t] = exp(-2*pi*i*t/400) (all threads of the CTA; sync afterwards)
+__device__ __forceinline__ void fft400_stage_tables(cplx* s_tw, const cplx* __restrict__ tw400) {
+    for (int i = threadIdx.x; i < kFft400TwLen; i += blockDim.x) {
+        int r, k, step;
+        if (i < 20) { r = i / 5 + 1; k = i % 5; step = 16; }                   // NS = 5, R = 5: 400 / 25
+        else if (i < 95) { r = (i - 20) / 25 + 1; k = (i - 20) % 25; step = 4; }   // NS = 25, R = 4: 400 / 100
+        else { r = (i - 95) / 100 + 1; k = (i - 95) % 100; step = 1; }         // NS = 100, R = 4
+        s_tw[i] = tw400[r * k * step];
+    }
+}
+
 template <int SIGN>
-__device__ __forceinline__ void fft400(cplx* a, cplx* b, const cplx* tw, int lane) {
-    stockham_stage<400, 5, 1, SIGN>(a, b, tw, lane);
-    stockham_stage<400, 5, 5, SIGN>(b, a, tw, lane);
-    stockham_stage<400, 4, 25, SIGN>(a, b, tw, lane);
-    stockham_stage<400, 4, 100, SIGN>(b, a, tw, lane);
+__device__ __forceinline__ void fft400(cplx* a, cplx* b, const cplx* tw_stage, int lane) {
+    stockham_stage<400, 5, 1, SIGN>(a, b, tw_stage, lane);
+    stockham_stage<400, 5, 5, SIGN, true>(b, a, tw_stage, lane);
+    stockham_stage<400, 4, 25, SIGN, true>(a, b, tw_stage + 20, lane);
+    stockham_stage<400, 4, 100, SIGN, true>(b, a, tw_stage + 95, lane);
 }
 
 template <int M, int SIGN> struct HalfFFT;

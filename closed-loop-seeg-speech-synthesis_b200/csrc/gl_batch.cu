@@ -54,7 +54,7 @@ k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restr
     cplx* s_work = reinterpret_cast<cplx*>(s_ring + kRingB * kN);           // per warp: a[400]
     double* s_exp = reinterpret_cast<double*>(s_work + kBW * kM);           // per warp: exp(logmel) [n_mels <= 64]
     for (int i = threadIdx.x; i < kN; i += blockDim.x) s_window[i] = tab.window[i];
-    for (int i = threadIdx.x; i < kM; i += blockDim.x) s_tw_half[i] = tab.tw_half[i];
+    fft400_stage_tables(s_tw_half, tab.tw_half);                             // [395] per-stage twiddles
     for (int i = threadIdx.x; i < kBinsB; i += blockDim.x) s_tw_full[i] = tab.tw_full[i];
     __syncthreads();
 
@@ -74,8 +74,11 @@ k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restr
                 cplx* b = reinterpret_cast<cplx*>(slot);                    // scratch until the frame's result is stored
                 for (int m = lane; m < n_mels; m += 32) ex[m] = exp(lm_u[(long long)n * n_mels + m]);
                 const double* xin = xu + (long long)n * kHopB;
-                for (int i = lane; i < kM; i += 32)
-                    a[i] = cplx{xin[2 * i] * s_window[2 * i], xin[2 * i + 1] * s_window[2 * i + 1]};
+                for (int i = lane; i < kM; i += 32) {
+                    const double2 xv = *reinterpret_cast<const double2*>(xin + 2 * i);
+                    const double2 wv = *reinterpret_cast<const double2*>(s_window + 2 * i);
+                    a[i] = cplx{xv.x * wv.x, xv.y * wv.y};
+                }
                 __syncwarp();
                 fft400<-1>(a, b, s_tw_half, lane);
                 // real-FFT split, phase projection Z = S * X/|X|, and the inverse split, bin pairs (k, 400-k) together
@@ -127,8 +130,9 @@ k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restr
                 __syncwarp();
                 fft400<+1>(a, b, s_tw_half, lane);
                 for (int i = lane; i < kM; i += 32) {
-                    slot[2 * i] = (a[i].x * scale) * s_window[2 * i];
-                    slot[2 * i + 1] = (a[i].y * scale) * s_window[2 * i + 1];
+                    const double2 wv = *reinterpret_cast<const double2*>(s_window + 2 * i);
+                    const cplx v = a[i];
+                    *reinterpret_cast<double2*>(slot + 2 * i) = make_double2((v.x * scale) * wv.x, (v.y * scale) * wv.y);
                 }
             }
             __syncthreads();
