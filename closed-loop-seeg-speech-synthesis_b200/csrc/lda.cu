@@ -116,12 +116,18 @@ template <int KC>
 __global__ void __launch_bounds__(512)
 k_lda_rows(const double* __restrict__ feat, const double* __restrict__ Wt, const double* __restrict__ bias,
            const double* __restrict__ cls, const int* __restrict__ select, const double* __restrict__ medians,
-           const double* __restrict__ taps, double* __restrict__ labels, double* __restrict__ spec, int smooth, const LdaGeom g) {
+           const double* __restrict__ taps, double* __restrict__ labels, double* __restrict__ spec, int smooth, const LdaGeom g,
+           const int* __restrict__ list, const int* __restrict__ list_count) {
     extern __shared__ double sm[];
     double* xs = sm;                                   // [F]
     double* score = xs + g.n_features;                 // [n_bins][KC]
     double* raw = score + g.n_bins * KC;               // [n_bins]
-    const int row = blockIdx.x, sess = blockIdx.y;
+    // list mode (exact re-scoring of the frames the tensor-core pass flagged; frame id = session * n_rows + row): a
+    // fixed grid strides over the list, whose length is only known on the device
+    const int n_list = list ? *list_count : 1;
+    for (int li = list ? blockIdx.x : 0; li < n_list; li += list ? gridDim.x : n_list) {
+    int row = blockIdx.x, sess = blockIdx.y;
+    if (list) { const int id = list[li]; sess = id / g.n_rows; row = id - sess * g.n_rows; }
     const double* fs = feat + (long long)sess * g.n_windows * g.n_channels;
     for (int f = threadIdx.x; f < g.n_features; f += blockDim.x) {
         const int col = select[f];
@@ -154,9 +160,8 @@ k_lda_rows(const double* __restrict__ feat, const double* __restrict__ Wt, const
         lv = lv < 0 ? 0 : (lv >= g.n_levels ? g.n_levels - 1 : lv);
         raw[b] = medians[b * g.n_levels + lv];
     }
-    if (!spec) return;
     __syncthreads();
-    for (int b = threadIdx.x; b < g.n_bins; b += blockDim.x) {
+    for (int b = threadIdx.x; spec && b < g.n_bins; b += blockDim.x) {
         double v = raw[b];
         if (smooth) {
             const int R = g.smooth_radius;
@@ -171,6 +176,8 @@ k_lda_rows(const double* __restrict__ feat, const double* __restrict__ Wt, const
         }
         spec[((long long)sess * g.n_rows + row) * g.n_bins + b] = v;
     }
+    __syncthreads();                                    // xs / score / raw are reused by the next list entry
+    }
 }
 
 constexpr long long kLdaRowsMax = 256;      // up to this many frames the per-frame kernel has the lower latency
@@ -182,11 +189,14 @@ int lda_run(const double* feat, const double* Wt, const double* bias, const doub
     const size_t smem = sizeof(double) * 33 * ((size_t)g.n_features + g.n_bins);
     if (smem > 200 * 1024) { set_error("too many features (%d) for the LDA kernel", g.n_features); return SGS_ERR_UNSUPPORTED; }
     if (g.n_classes != kMaxClasses) { set_error("LDA kernel is built for %d classes per bin (got %d)", kMaxClasses, g.n_classes); return SGS_ERR_UNSUPPORTED; }
-    if (!list && (long long)g.n_rows * n_sessions <= kLdaRowsMax) {
+    if (list || (long long)g.n_rows * n_sessions <= kLdaRowsMax) {
+        // few frames, or the flagged near-ties of the tensor-core pass (a few dozen of 1.9 M frames in the bench: with 32
+        // frames per block only two blocks of the batch kernel had work, 0.6 ms of exposed L2 latency)
         const int threads = 384;
         const size_t sm_rows = sizeof(double) * ((size_t)g.n_features + (size_t)g.n_bins * (kMaxClasses + 1));
         if (sm_rows > 48 * 1024) { set_error("too many features (%d) for the per-frame LDA kernel", g.n_features); return SGS_ERR_UNSUPPORTED; }
-        { ProfScope ps(kProfLda, st); k_lda_rows<kMaxClasses><<<dim3(g.n_rows, n_sessions), threads, sm_rows, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g); }
+        const dim3 grid_rows = list ? dim3((unsigned)std::min<long long>(std::max<long long>(list_cap, 1), 148 * 4), 1) : dim3(g.n_rows, n_sessions);
+        { ProfScope ps(kProfLda, st); k_lda_rows<kMaxClasses><<<grid_rows, threads, sm_rows, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g, list, list_count); }
         SGS_LAUNCHED();
         SGS_CUDA(cudaGetLastError());
         return SGS_OK;
@@ -194,7 +204,6 @@ int lda_run(const double* feat, const double* Wt, const double* bias, const doub
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lda_decode<kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     dim3 grid(ceil_div(g.n_rows, kLdaFrames), n_sessions);
-    if (list) grid = dim3((int)std::min<long long>(ceil_div(list_cap, kLdaFrames), 148 * 8), 1);   // strides over the list
     { ProfScope ps(kProfLda, st); k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g, list, list_count); }
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
