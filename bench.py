@@ -47,11 +47,12 @@ def random_model(rng, n_feat_total, n_bins=40, n_classes=9, n_sel=150):
 
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons of one GPU read through NVML - from the MAIN thread, right after the kernels of
-    the middle and of the last timed step have been enqueued (the device is then busy with them for ~94 ms, so the samples are
-    taken during the timed region).  NVML queries pause the device: the first ones of a process by 100-500 ms (paid during the
-    warm-up), later ones occasionally by tens of ms, hence only two.  Asynchronous sampling (an `nvidia-smi -lms` child at first, then a pynvml thread) made the first timed step
-    take 115-540 ms instead of 94 in most runs - a query that lands in the idle gap after the warm-up's synchronize - while
-    runs without any sampler never did (0 of 6 against 5 of 6, same box, same code)."""
+    the middle and of the last timed step have been enqueued (the device is then busy with them for ~85 ms, so the samples are
+    taken during the timed region).  The first queries of an NVML client take 100-500 ms and are paid at construction and in
+    the first warm-up step; later ones cost the step they land in 0-2 ms, hence only two.  (Sporadic first timed steps of
+    100-540 ms were first blamed on asynchronous sampling - an `nvidia-smi -lms` child, then a pynvml thread - but persisted
+    without any sampler: the cause was a full pass of Python's cyclic collector at the start of the timed region, where the
+    device queue is empty and a host pause is exposed; see run_ours.)"""
     REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, device_index):
@@ -161,15 +162,25 @@ def run_ours(args):
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # the device queue is empty when the first timed step starts, so a host pause there is not hidden behind queued work as
+    # it is in the later steps: keep the cyclic collector out of the timed region (a full collection in this process takes
+    # tens of ms; 2 of 5 runs showed a first step of 103-113 ms instead of 84 with the collector on, kernels unchanged)
+    import gc
+    gc.collect()
+    gc.disable()
+    host_t = []
     barrier()
     ev0.record()
     for k in range(args.steps):
+        h0 = time.perf_counter()
         out = step()
+        host_t.append(time.perf_counter() - h0)
         marks[k].record()
         if sampler is not None and k in (args.steps // 2, args.steps - 1):
             sampler.sample()               # the device is still executing step k; two samples only: a query can pause the device
     ev1.record()
     barrier()
+    gc.enable()
     ms = ev0.elapsed_time(ev1)
     step_ms = [(ev0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(args.steps)]
     launches = _lib.launch_count() - n0
@@ -261,6 +272,7 @@ def run_ours(args):
                  "unit": "TFLOP/s issued (3 split-TF32 products, padded 160 x 384; kernel time from profiles/launches_r01e.txt; peak = half the measured bf16 rate)"}],
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "ms_each_step": [round(v, 3) for v in step_ms],
+            "host_enqueue_ms_each_step": [round(v * 1e3, 3) for v in host_t],
             "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
             "clocks": sampler.summary() if sampler is not None else None,
         }
@@ -355,18 +367,34 @@ def latency_leg(seconds=30.0, paced_seconds=8.0):
         rec_seeg, rec_spec, rec_audio = dec_mod.setup_decoder(src, SR, pickle.dumps(ests), medians, [], select, gl_norm=10,
                                                              packet_size=packet, include_soundcard=False)
         lat, last, t_in = [], [], [0.0]
+        push_wall = []
+        if os.environ.get('SGS_LAT_TRACE'):               # where a slow packet spends its time: the C call or the Python around it
+            from sgs import chain as chain_mod
+            if not hasattr(chain_mod.FusedChain, '_orig_push'):
+                chain_mod.FusedChain._orig_push = chain_mod.FusedChain.push
+
+            def timed_push(self, block, ends, idx, _w=push_wall):
+                t0 = time.perf_counter()
+                r = chain_mod.FusedChain._orig_push(self, block, ends, idx)
+                _w.append(time.perf_counter() - t0)
+                return r
+            chain_mod.FusedChain.push = timed_push
         gl_node = rec_audio.get_inputs()[0]
         gl_node.add_output(lambda f: lat.append(time.perf_counter() - t_in[0]))
         gc.collect()
         gc.disable()
         try:
+            trace = []
             for i in range(0, len(x) - packet + 1, packet):
                 chunk = np.array(x[i:i + packet])
-                n0 = len(lat)
+                n0, w0 = len(lat), len(push_wall)
                 t_in[0] = time.perf_counter()
                 src.output_data(chunk)
+                t_all = time.perf_counter() - t_in[0]
                 if len(lat) > n0:
                     last.append(lat[-1])
+                    if push_wall:
+                        trace.append((t_all, sum(push_wall[w0:]), lat[-1]))
         finally:
             gc.enable()
         lat_ms, last_ms = np.array(lat[100:]) * 1e3, np.array(last[30:]) * 1e3
@@ -376,6 +404,13 @@ def latency_leg(seconds=30.0, paced_seconds=8.0):
             "max_ms": float(lat_ms.max()),
             "last_frame_of_packet": {"p50_ms": float(np.percentile(last_ms, 50)), "p99_ms": float(np.percentile(last_ms, 99))},
             "packets_over_1.6x_median": {"count": int(len(slow)), "of": int(len(last_ms)), "first_indices": slow[:12].tolist()}}
+        if trace:
+            tr = np.array(trace[30:]) * 1e3
+            med = np.median(tr, axis=0)
+            sl = tr[tr[:, 2] > 1.6 * med[2]]
+            out["packet_%d" % packet]["trace_ms"] = {
+                "columns": ["whole output_data call", "C chain push inside it", "until the last audio callback"],
+                "median": np.round(med, 3).tolist(), "slow_packets_mean": np.round(sl.mean(axis=0), 3).tolist() if len(sl) else None}
         if packet == 64 and paced_seconds > 0:
             # the same graph fed in real time (one packet every 31.25 ms, the device idle in between), as a closed-loop
             # set-up delivers them; the back-to-back feed above measures the chain, this one adds the wake-up of an idle GPU

@@ -1,5 +1,5 @@
 """Runs `python bench.py` N times and prints the per-step times of each run (run-to-run stability of the timed region).
-Usage: python tools/bench_repeat.py [N] [tag]  -> gpurun_out/bench_<tag>_<i>.log"""
+Usage: python tools/bench_repeat.py [N] [tag] [bench.py arguments...]  -> gpurun_out/bench_<tag>_<i>.log"""
 import json
 import os
 import subprocess
@@ -16,7 +16,8 @@ for i in range(1, n + 1):
     line = open(log).read().strip().splitlines()[-1]
     try:
         d = json.loads(line)
-        print(rc, round(d['value']), d['ms_each_step'], round(d['e2e']['value']), round(d['latency']['p99_ms'], 3), d['clocks']['sm_mhz'],
-              d['clocks']['reasons'], flush=True)
+        lat = d.get('latency') or {}
+        clk = d.get('clocks') or {}
+        print(rc, round(d['value']), d['ms_each_step'], d.get('host_enqueue_ms_each_step'), round(d['e2e']['value']), lat.get('p99_ms'), clk.get('sm_mhz'), clk.get('reasons'), flush=True)
     except ValueError:
         print(rc, line[-300:], flush=True)
