@@ -139,6 +139,19 @@ def run_ours(args):
     def step():
         return dec_mod.decode_sessions(decoder, x, seed=11)
 
+    stage_t = []
+    if os.environ.get('SGS_BENCH_TRACE_STEP'):            # host time of each of the three operator calls of a step (diagnosis)
+        def wrap(obj, name):
+            orig = getattr(obj, name)
+
+            def timed(*a, **kw):
+                t0 = time.perf_counter()
+                r = orig(*a, **kw)
+                stage_t.append((name, round((time.perf_counter() - t0) * 1e3, 3)))
+                return r
+            setattr(obj, name, timed)
+        wrap(decoder.features, 'log_power'); wrap(decoder.lda, 'decode'); wrap(decoder.gl, 'synthesize')
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -169,6 +182,7 @@ def run_ours(args):
     gc.collect()
     gc.disable()
     host_t = []
+    del stage_t[:]
     barrier()
     ev0.record()
     for k in range(args.steps):
@@ -273,6 +287,7 @@ def run_ours(args):
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "ms_each_step": [round(v, 3) for v in step_ms],
             "host_enqueue_ms_each_step": [round(v * 1e3, 3) for v in host_t],
+            "host_stage_ms_first_two_steps": stage_t[:6] or None,
             "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
             "clocks": sampler.summary() if sampler is not None else None,
         }
@@ -373,10 +388,17 @@ def latency_leg(seconds=30.0, paced_seconds=8.0):
             if not hasattr(chain_mod.FusedChain, '_orig_push'):
                 chain_mod.FusedChain._orig_push = chain_mod.FusedChain.push
 
+            from sgs import _lib as lib_mod
+            lib_mod.profile_enable(True)
+            classes = ('stream', 'lda', 'gl_blocks', 'gl_ola')
+            dev_ms = []
+
             def timed_push(self, block, ends, idx, _w=push_wall):
+                before = [lib_mod.profile_read(c)[0] for c in classes]
                 t0 = time.perf_counter()
                 r = chain_mod.FusedChain._orig_push(self, block, ends, idx)
                 _w.append(time.perf_counter() - t0)
+                dev_ms.append([lib_mod.profile_read(c)[0] - b for c, b in zip(classes, before)])
                 return r
             chain_mod.FusedChain.push = timed_push
         gl_node = rec_audio.get_inputs()[0]
@@ -394,7 +416,7 @@ def latency_leg(seconds=30.0, paced_seconds=8.0):
                 if len(lat) > n0:
                     last.append(lat[-1])
                     if push_wall:
-                        trace.append((t_all, sum(push_wall[w0:]), lat[-1]))
+                        trace.append((t_all, sum(push_wall[w0:]), lat[-1]) + tuple(1e-3 * sum(d[j] for d in dev_ms[w0:]) for j in range(4)))
         finally:
             gc.enable()
         lat_ms, last_ms = np.array(lat[100:]) * 1e3, np.array(last[30:]) * 1e3
@@ -409,7 +431,8 @@ def latency_leg(seconds=30.0, paced_seconds=8.0):
             med = np.median(tr, axis=0)
             sl = tr[tr[:, 2] > 1.6 * med[2]]
             out["packet_%d" % packet]["trace_ms"] = {
-                "columns": ["whole output_data call", "C chain push inside it", "until the last audio callback"],
+                "columns": ["whole output_data call", "C chain push inside it", "until the last audio callback",
+                            "device: stream kernels", "device: lda", "device: gl_blocks", "device: gl_ola / emit"],
                 "median": np.round(med, 3).tolist(), "slow_packets_mean": np.round(sl.mean(axis=0), 3).tolist() if len(sl) else None}
         if packet == 64 and paced_seconds > 0:
             # the same graph fed in real time (one packet every 31.25 ms, the device idle in between), as a closed-loop

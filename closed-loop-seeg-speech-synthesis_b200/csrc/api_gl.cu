@@ -46,7 +46,30 @@ struct sgs_gl_node {
     std::vector<int32_t> h_pos;
     int* d_pos = nullptr;
     size_t d_pos_cap = 0;
+    // scratch of sgs_gl_node_synthesize (blocks, overlap-added waveform, low-pass chunk states), one arena per stream, kept
+    // between calls: at 32 sessions x 60 000 frames this is 10 GB, and taking it from the stream-ordered pool on every call
+    // cost 6 ms of host time - 20 to 400 ms on the first call after a device synchronize, when the queue behind it is empty
+    struct Arena { cudaStream_t st; char* p; size_t cap; };
+    std::vector<Arena> arenas;
 };
+
+// the stream's arena, grown (never shrunk) to `bytes`; growing waits for the stream's earlier work
+static cudaError_t gl_arena(sgs_gl_node* n, cudaStream_t st, size_t bytes, char** out) {
+    sgs_gl_node::Arena* a = nullptr;
+    for (auto& it : n->arenas) if (it.st == st) a = &it;
+    if (!a) { n->arenas.push_back({st, nullptr, 0}); a = &n->arenas.back(); }
+    if (a->cap < bytes) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return e;
+        if (a->p) cudaFree(a->p);
+        a->p = nullptr; a->cap = 0;
+        e = cudaMalloc((void**)&a->p, bytes);
+        if (e != cudaSuccess) return e;
+        a->cap = bytes;
+    }
+    *out = a->p;
+    return cudaSuccess;
+}
 
 static cudaError_t upload(void** dst, const void* src, size_t bytes) {
     cudaError_t e = cudaMalloc(dst, bytes);
@@ -61,6 +84,7 @@ void sgs_gl_node_destroy(sgs_gl_node* n) {
     cudaFree(n->d_window); cudaFree(n->d_ola); cudaFree(n->d_inv_w); cudaFree(n->d_phi); cudaFree(n->d_phi_sub);
     cudaFree(n->d_tw_full); cudaFree(n->d_tw_t); cudaFree(n->d_inv_idx);
     cudaFree(n->d_mel); cudaFree(n->d_ring); cudaFree(n->d_lp); cudaFree(n->d_noise); cudaFree(n->d_pcm); cudaFree(n->d_pos);
+    for (auto& a : n->arenas) cudaFree(a.p);
     delete n;
 }
 
@@ -173,13 +197,21 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
     if (rc == SGS_OK && filtered) rc = stage_out(s_flt, filtered, sizeof(double) * (size_t)n_sessions * n_out, st);
     if (rc == SGS_OK) rc = stage_out(s_blk, blocks_out, blocks_out ? sizeof(double) * (size_t)n_sessions * n_frames * kBlk : 0, st);
     double* d_blocks = (double*)s_blk.dev;
-    bool own_blocks = false;
     cudaError_t e = cudaSuccess;
     if (rc == SGS_OK) {
-        if (!d_blocks) { e = cudaMallocAsync((void**)&d_blocks, sizeof(double) * (size_t)n_sessions * n_frames * kBlk, st); own_blocks = true; }
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_v, sizeof(double) * (size_t)n_sessions * n_out, st);
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_states, sizeof(double) * 2 * (size_t)n_sessions * n_chunks * kLpMaxOrd, st);
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_zi, sizeof(double) * 2 * (size_t)n_sessions * ord, st);   // in, out
+        auto pad = [](size_t b) { return (b + 255) / 256 * 256; };
+        const size_t b_blocks = d_blocks ? 0 : pad(sizeof(double) * (size_t)n_sessions * n_frames * kBlk);
+        const size_t b_v = pad(sizeof(double) * (size_t)n_sessions * n_out);
+        const size_t b_states = pad(sizeof(double) * 2 * (size_t)n_sessions * n_chunks * kLpMaxOrd);
+        const size_t b_zi = pad(sizeof(double) * 2 * (size_t)n_sessions * ord);                                        // in, out
+        char* arena = nullptr;
+        e = gl_arena(n, st, b_blocks + b_v + b_states + b_zi, &arena);
+        if (e == cudaSuccess) {
+            if (!d_blocks) d_blocks = (double*)arena;
+            d_v = (double*)(arena + b_blocks);
+            d_states = (double*)(arena + b_blocks + b_v);
+            d_zi = (double*)(arena + b_blocks + b_v + b_states);
+        }
         if (e == cudaSuccess)
             e = lp_state ? cudaMemcpyAsync(d_zi, zi_host.data(), sizeof(double) * n_sessions * ord, cudaMemcpyHostToDevice, st)
                          : cudaMemsetAsync(d_zi, 0, sizeof(double) * n_sessions * ord, st);
@@ -203,10 +235,6 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
         else memcpy(lp_state, zi_host.data(), sizeof(double) * n_sessions * ord);
     }
     const bool sync = s_pcm.host || s_flt.host || s_blk.host;
-    if (own_blocks && d_blocks) cudaFreeAsync(d_blocks, st);
-    if (d_v) cudaFreeAsync(d_v, st);
-    if (d_states) cudaFreeAsync(d_states, st);
-    if (d_zi) cudaFreeAsync(d_zi, st);
     release(s_mel, st); release(s_noise, st); release(s_pcm, st); release(s_flt, st); release(s_blk, st);
     if (rc == SGS_OK && sync) SGS_CUDA(cudaStreamSynchronize(st));
     return rc;

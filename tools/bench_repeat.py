@@ -18,6 +18,6 @@ for i in range(1, n + 1):
         d = json.loads(line)
         lat = d.get('latency') or {}
         clk = d.get('clocks') or {}
-        print(rc, round(d['value']), d['ms_each_step'], d.get('host_enqueue_ms_each_step'), round(d['e2e']['value']), lat.get('p99_ms'), clk.get('sm_mhz'), clk.get('reasons'), flush=True)
+        print(rc, round(d['value']), d['ms_each_step'], d.get('host_enqueue_ms_each_step'), d.get('host_stage_ms_first_two_steps'), round(d['e2e']['value']), lat.get('p99_ms'), clk.get('sm_mhz'), clk.get('reasons'), flush=True)
     except ValueError:
         print(rc, line[-300:], flush=True)
