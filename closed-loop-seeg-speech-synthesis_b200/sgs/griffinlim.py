@@ -61,11 +61,15 @@ class GriffinLimNodeOp:
     def positions(self, n_frames, start_ms=0.0):
         """Write-head position after each frame, with the node's float expression (GriffinLim.py:115-120)."""
         p = self.plan
-        pos = np.empty(n_frames, dtype=np.int32)
-        ms = start_ms
-        for k in range(n_frames):
-            ms += p.frame_shift_ms
-            pos[k] = int((ms / 1000.0) * p.sample_rate)
+        key = (int(n_frames), float(start_ms))
+        cached = getattr(self, '_pos_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        # ms += frame_shift_ms per frame: np.cumsum adds sequentially in float64, i.e. the same roundings as the node's loop
+        ms = np.cumsum(np.concatenate([[float(start_ms)], np.full(n_frames, float(p.frame_shift_ms))]))[1:]
+        pos = ((ms / 1000.0) * p.sample_rate).astype(np.int64).astype(np.int32)
+        pos.setflags(write=False)                              # shared between calls
+        self._pos_cache = (key, pos)
         return pos
 
     def synthesize(self, logmel, noise=None, seed=0, want_filtered=False, want_blocks=False):
