@@ -76,7 +76,7 @@ int sgs_chain_push(sgs_chain* c, const void* x, int x_is_f64, int n, const int64
     double* d_labels = (double*)(c->d_out + o_labels);
     double* d_spec = (double*)(c->d_out + o_spec);
     short* d_pcm = (short*)(c->d_out + o_pcm);
-    int rc = feat_stream_enqueue(c->feat, c->h_in + c->in_x, x_is_f64, n, frame_ends, frame_index, n_frames, d_rows, st);
+    int rc = feat_stream_enqueue(c->feat, c->h_in + c->in_x, x_is_f64, n, frame_ends, frame_index, n_frames, d_rows, st, true);
     if (rc != SGS_OK) return rc;
     if (n_pcm) *n_pcm = 0;
     if (n_frames == 0) { SGS_CUDA(cudaEventRecord(c->in_consumed, st)); return SGS_OK; }                 // nothing to read back: the packet only advanced the filter state
@@ -84,7 +84,7 @@ int sgs_chain_push(sgs_chain* c, const void* x, int x_is_f64, int n, const int64
     if (rc != SGS_OK) return rc;
     int total = 0;
     rc = gl_node_enqueue(c->gl, d_spec, n_frames, gl_pos, gl_pos_before, noise ? (const double*)(c->h_in + c->in_noise) : nullptr,
-                         seed, d_pcm, &total, st);
+                         seed, d_pcm, &total, st, true);
     if (rc != SGS_OK) return rc;
     // one read-back of everything the four nodes emit for this packet
     const size_t used = o_pcm + sizeof(short) * (size_t)total;

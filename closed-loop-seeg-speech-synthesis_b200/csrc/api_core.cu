@@ -53,6 +53,24 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return SGS_ERR_CUDA;
 }
 
+__global__ void k_copy_in16(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16) dst[i] = src[i];
+}
+
+int copy_in_small(void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st) {
+    if (bytes == 0) return SGS_OK;
+    if (src_pinned && bytes % 16 == 0 && ((uintptr_t)dst | (uintptr_t)src) % 16 == 0 && bytes <= (1u << 20)) {
+        const size_t n16 = bytes / 16;
+        k_copy_in16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((uint4*)dst, (const uint4*)src, n16);   // UVA: the pinned host pointer is valid on the device
+        SGS_LAUNCHED();
+        SGS_CUDA(cudaGetLastError());
+        return SGS_OK;
+    }
+    SGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+    return SGS_OK;
+}
+
 bool is_device_ptr(const void* p) {
     if (!p) return false;
     cudaPointerAttributes a;

@@ -281,7 +281,7 @@ int feat_stream_row_width(const sgs_feat_stream* s) { return s->n_channels * (s-
 /* Everything of a push except the read-back: copy the new samples (host or device) into the stream's staging
  * buffer and launch k_feat_stream; the stacked rows land in d_rows (or the stream's own buffer when NULL). */
 int feat_stream_enqueue(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
-                        const int64_t* frame_index, int n_frames, double* d_rows, cudaStream_t st) {
+                        const int64_t* frame_index, int n_frames, double* d_rows, cudaStream_t st, bool src_pinned) {
     SGS_ARG(s && x && n >= 1, "bad arguments");
     SGS_ARG(n_frames >= 0 && n_frames <= kMaxFramesPerPush && (n_frames == 0 || (frame_ends && frame_index)), "bad frame schedule");
     SGS_ARG(n <= 128, "push at most 128 samples per call (got %d)", n);
@@ -299,8 +299,9 @@ int feat_stream_enqueue(sgs_feat_stream* s, const void* x, int x_is_f64, int n, 
         fr.end[q] = frame_ends[q];
         fr.index[q] = frame_index[q];
     }
-    SGS_CUDA(cudaMemcpyAsync(s->d_x, x, bytes, cudaMemcpyDefault, st));
-    int rc = feat_stream_run(s->plan->n_biquads, s->d_x, x_is_f64 != 0, n, s->n_channels, s->consumed, s->d_z, s->d_sq, s->d_feat,
+    int rc = copy_in_small(s->d_x, x, bytes, src_pinned, st);
+    if (rc != SGS_OK) return rc;
+    rc = feat_stream_run(s->plan->n_biquads, s->d_x, x_is_f64 != 0, n, s->n_channels, s->consumed, s->d_z, s->d_sq, s->d_feat,
                              s->plan->d_zf, s->plan->zero_fill, s->frame_size, s->order, s->step, d_rows ? d_rows : s->d_out,
                              s->plan->cf, fr, st);
     if (rc != SGS_OK) return rc;

@@ -352,14 +352,14 @@ namespace sgs {
 /* Everything of a node push except the read-back: logmel / noise may be host or device memory; the int16 hop(s) land in
  * d_pcm (or the node's own buffer when NULL); *n_pcm = number of samples emitted. */
 int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
-                    uint64_t seed, short* d_pcm, int* n_pcm, cudaStream_t st) {
+                    uint64_t seed, short* d_pcm, int* n_pcm, cudaStream_t st, bool src_pinned) {
     SGS_ARG(s && logmel && pos && n_pcm, "NULL argument");
     SGS_ARG(n >= 1 && n <= kMaxFramesPerPush, "push takes 1..%d frames (got %d)", kMaxFramesPerPush, n);
     const int nm = s->n_mels, first = s->first_frame;
     const long long k0 = s->frames_seen;
     // row 0 of d_mel holds the previous frame; append the new ones behind it
     SGS_CUDA(cudaMemcpyAsync(s->d_mel + nm, logmel, sizeof(double) * n * nm, cudaMemcpyDefault, st));
-    if (noise) SGS_CUDA(cudaMemcpyAsync(s->d_noise + kBlk, noise, sizeof(double) * n * kBlk, cudaMemcpyDefault, st));
+    if (noise) { const int rcn = copy_in_small(s->d_noise + kBlk, noise, sizeof(double) * n * kBlk, src_pinned, st); if (rcn != SGS_OK) return rcn; }
     EmitFrames fr;
     memset(&fr, 0, sizeof(fr));
     int total = 0, prev = pos_before;

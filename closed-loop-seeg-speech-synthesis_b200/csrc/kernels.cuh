@@ -115,12 +115,16 @@ int lda_stats_tc_run(const double* x, long long n, long long row_stride, const i
 
 // ---- streaming handles driven back to back by the fused chain (api_feat.cu, api_lda.cu, api_gl.cu -> api_chain.cu) -----------------
 int feat_stream_row_width(const sgs_feat_stream* s);
+// small host-to-device copy of the streaming path.  From page-locked memory (src_pinned) a copy kernel reads the mapped
+// host buffer over PCIe instead of a cudaMemcpyAsync, which keeps the packet on the compute queue (no copy-engine hand-over):
+// median packet latency 0.237 -> 0.226 ms (64-sample packets), 0.190 -> 0.185 ms (32).
+int copy_in_small(void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st);
 int feat_stream_enqueue(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
-                        const int64_t* frame_index, int n_frames, double* d_rows, cudaStream_t st);
+                        const int64_t* frame_index, int n_frames, double* d_rows, cudaStream_t st, bool src_pinned = false);
 int lda_model_bins(const sgs_lda_model* m);
 int lda_rows_enqueue(const sgs_lda_model* m, const double* d_rows, int n_rows, int row_width, double* d_labels, double* d_spec,
                      int smooth, cudaStream_t st);
 int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
-                    uint64_t seed, short* d_pcm, int* n_pcm, cudaStream_t st);
+                    uint64_t seed, short* d_pcm, int* n_pcm, cudaStream_t st, bool src_pinned = false);
 
 }  // namespace sgs
