@@ -1,5 +1,6 @@
 """Host-side tables and runtime on CPU: window schedules, mel tables, scan planning, the Node callback runtime."""
 import os
+import time
 
 import numpy as np
 import pytest
@@ -247,3 +248,18 @@ def test_exp_angle_tables_match_generator():
         worst = max(worst, float(abs(val / mp.exp(mp.atan2(mp.mpf(y), mp.mpf(x))) - 1)))
         assert abs(s) <= 0.0635
     assert worst < 1.5 * 2.2e-16
+
+
+def test_receiver_timed_flush_runs_off_the_graph_thread():
+    """Timed hand-overs go through the flusher thread; order is kept and a synchronous flush drains the queue first."""
+    import threading
+    from livenodes import Receiver
+    rec = Receiver.Receiver(flush_interval=0.01)
+    for i in range(60):
+        rec.add_data(i)
+        time.sleep(0.002)
+    assert rec._thread is not None and rec._thread.name.endswith('-flusher') and rec._thread is not threading.current_thread()
+    assert rec.get_data() == list(range(60))
+    rec.add_data(60)
+    rec.stop_processing()
+    assert list(rec.data) == list(range(61))
