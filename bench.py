@@ -282,8 +282,8 @@ def run_ours(args):
                  "peak": 2 * FP64_PEAK, "unit": "fp64 flop/s (164 kflop nominal per 10 ms frame, SURVEY.md 8d)",
                  "note": "pipe busy 54 % by ncu (profiles/ncu_gl_blocks8_r01b.txt), bound by dependent latency at 4 warps per scheduler; the nominal 5 N log2 N count leaves out exp(angle) and the splits"},
                 {"kernel": "k_lda_tc (LDA scoring, tcgen05 kind::tf32)", "bound": "tensor",
-                 "achieved": (2.0 * S * n_frames * 160 * 384 * 3 / 1e12 / (1.796e-3 * S / 32)), "peak": 0.5 * float(peaks.get('bf16_tflops', 1650.6)),
-                 "unit": "TFLOP/s issued (3 split-TF32 products, padded 160 x 384; kernel time from profiles/launches_r01e.txt; peak = half the measured bf16 rate)"}],
+                 "achieved": (2.0 * S * n_frames * 160 * 384 * 3 / 1e12 / (1.769e-3 * S / 32)), "peak": 0.5 * float(peaks.get('bf16_tflops', 1650.6)),
+                 "unit": "TFLOP/s issued (3 split-TF32 products, padded 160 x 384; kernel time from profiles/launches_r01f.txt; peak = half the measured bf16 rate)"}],
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "ms_each_step": [round(v, 3) for v in step_ms],
             "host_enqueue_ms_each_step": [round(v * 1e3, 3) for v in host_t],
