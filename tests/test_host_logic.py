@@ -263,3 +263,19 @@ def test_receiver_timed_flush_runs_off_the_graph_thread():
     rec.add_data(60)
     rec.stop_processing()
     assert list(rec.data) == list(range(61))
+
+
+def test_gl_write_head_table_equals_the_node_loop():
+    """GriffinLimNodeOp.positions (cumsum, cached) reproduces the node's per-frame float accumulation
+    `outputBufferPosMs += frameShiftMs; pos = int(ms / 1000 * sampleRate)` (GriffinLim.py:115-120) bit for bit."""
+    from sgs.griffinlim import GriffinLimNodeOp
+    for shift in (10, 10.0, 9.97):
+        op = GriffinLimNodeOp(16, shift, 16000, 40)
+        for start in (0.0, 3.3):
+            got = op.positions(70000, start)
+            ms, want = start, np.empty(70000, dtype=np.int32)
+            for k in range(70000):
+                ms += op.plan.frame_shift_ms
+                want[k] = int((ms / 1000.0) * op.plan.sample_rate)
+            assert np.array_equal(got, want)
+            assert op.positions(70000, start) is got and not got.flags.writeable       # cached, shared, read-only
