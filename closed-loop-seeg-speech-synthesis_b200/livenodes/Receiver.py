@@ -31,6 +31,7 @@ class Receiver(Node.Node):
         self._last_flush = 0.0
         self._queue = None
         self._thread = None
+        self._unsent = []
 
     def _adopt_process(self):
         """First frame seen in this process (possibly a forked child): start a fresh local batch and make sure it is
@@ -40,15 +41,16 @@ class Receiver(Node.Node):
         self._last_flush = time.time()
         self._queue = None                  # threads do not survive a fork: the flusher starts with the first timed hand-over
         self._thread = None
+        self._unsent = []
         multiprocessing.util.Finalize(self, self.flush, exitpriority=100)
 
     def _flusher(self, q):
         while True:
             batch = q.get()
             try:
-                if batch is None:
-                    return
                 self.data.extend(batch)
+            except Exception:                # keep the frames; the next synchronous flush retries and reports
+                self._unsent.append(batch)
             finally:
                 q.task_done()
 
@@ -76,8 +78,11 @@ class Receiver(Node.Node):
         if self._local_pid == os.getpid():
             if self._thread is not None:
                 self._queue.join()
+            pending, self._unsent = self._unsent, []
             if self._local:
-                batch, self._local = self._local, []
+                pending.append(self._local)
+                self._local = []
+            for batch in pending:
                 self.data.extend(batch)
         self._last_flush = time.time()
 
