@@ -291,7 +291,7 @@ def run_ours(args):
             "lda_frames_rescored_fp64": [decoder.lda.last_rescored(), S * n_frames],
             "clocks": sampler.summary() if sampler is not None else None,
         }
-        line["cpu_baseline"] = cpu_baseline_sample()
+        line["cpu_baseline"] = cpu_baseline_sample() if world == 1 else None      # rank 0 at N = 1 only (the other ranks would wait for it)
         line["latency"] = latency_leg() if world == 1 and not args.no_latency else None
         print(json.dumps(line), flush=True)
     if world > 1:
