@@ -16,7 +16,7 @@ static cudaEvent_t g_open[kProfCount];
 static double g_prof_ms[kProfCount];
 static unsigned long long g_prof_n[kProfCount];
 static const char* kProfNames[kProfCount] = {"iir_init", "iir_state", "iir_carry", "iir_feat", "stack", "lda", "gl_blocks", "gl_ola",
-                                             "lowpass", "stream", "gl_batch", "logmel", "train", "lda_tc", "train_tc"};
+                                             "lowpass", "stream", "gl_batch", "logmel", "train", "lda_tc", "train_tc", "iir_pieces_state", "iir_pieces_feat", "lda_pack"};
 
 void prof_begin(int id, cudaStream_t st) {
     cudaEvent_t e;
@@ -154,7 +154,9 @@ int sgs_init(int device) {
 }
 
 /* Kernel-class timing: enable, run, then read.  name in {iir_init, iir_state, iir_carry, iir_feat, stack, lda, gl_blocks,
- * gl_ola, lowpass, stream, gl_batch, logmel, train}. */
+ * gl_ola, lowpass, stream, gl_batch, logmel, train, lda_tc, train_tc, iir_pieces_state, iir_pieces_feat, lda_pack}.
+ * iir_state / iir_feat time the (group x chunk) grid of k_iir_stages, iir_pieces_* the balanced-pieces kernel k_iir_pieces:
+ * a non-zero launch count of a class proves which decomposition ran. */
 int sgs_profile_enable(int on) {
     sgs::prof_collect();
     sgs::g_prof_on = on != 0;

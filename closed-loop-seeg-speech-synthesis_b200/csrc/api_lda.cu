@@ -107,7 +107,7 @@ int sgs_lda_model_create(sgs_lda_model** model, int n_bins, int n_classes, int n
                     wn[(size_t)s * 16 + (b - slice_bins[s])] = std::max(wn[(size_t)s * 16 + (b - slice_bins[s])], sqrt(nrm));
                 }
         if (e == cudaSuccess) e = up((void**)&m->d_wnorm, wn.data(), wn.size() * sizeof(double));
-        e = up((void**)&m->d_Bmat, B.data(), B.size() * sizeof(float));
+        if (e == cudaSuccess) e = up((void**)&m->d_Bmat, B.data(), B.size() * sizeof(float));
         if (e == cudaSuccess) e = up((void**)&m->d_cls_tc, cls_tc.data(), cls_tc.size() * sizeof(double));
         if (e == cudaSuccess) e = up((void**)&m->d_slice_bins, slice_bins, sizeof(slice_bins));
         if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_bias_tc, sizeof(double) * kTcSlices * kTcN);

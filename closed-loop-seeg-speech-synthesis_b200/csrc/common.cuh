@@ -48,7 +48,7 @@ void release(Staged& s, cudaStream_t st);
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
 enum ProfId { kProfIirInit = 0, kProfIirState, kProfIirCarry, kProfIirFeat, kProfStack, kProfLda, kProfGlBlocks, kProfGlOla,
-              kProfLowpass, kProfStream, kProfGlBatch, kProfLogMel, kProfTrain, kProfLdaTc, kProfTrainTc, kProfCount };
+              kProfLowpass, kProfStream, kProfGlBatch, kProfLogMel, kProfTrain, kProfLdaTc, kProfTrainTc, kProfPiecesState, kProfPiecesFeat, kProfLdaPack, kProfCount };
 extern bool g_prof_on;
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);
@@ -57,6 +57,20 @@ struct ProfScope {
     ProfScope(int i, cudaStream_t s) : id(i), st(s) { if (g_prof_on) prof_begin(id, st); }
     ~ProfScope() { if (g_prof_on) prof_end(id, st); }
 };
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so it
+// is set once per DEVICE - a process that calls sgs_init() for a second device must not inherit the first one's flag - and
+// its status is returned (a launch without the opt-in fails with invalid-value).  `done` = a static bit mask owned by the caller.
+template <typename F>
+static inline cudaError_t smem_optin(F* func, size_t bytes, unsigned long long* done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((*done >> dev) & 1ULL)) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && dev < 64) *done |= 1ULL << dev;
+    return e;
+}
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

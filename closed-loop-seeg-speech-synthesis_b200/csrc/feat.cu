@@ -396,11 +396,8 @@ static void run_all(const TIn* x, double* feat, double* slots, const double* phi
     const int bx = ceil_div(g.n_streams, kStreamsPerBlock);
     constexpr int hand_bytes = (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
     constexpr int feat_bytes = hand_bytes + RING * 32 * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_iir_stages<NB, MONIC, kModeFeat, RING, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, feat_bytes);
-        attr_set = true;
-    }
+    static unsigned long long optin = 0;
+    if (smem_optin(k_iir_stages<NB, MONIC, kModeFeat, RING, TIn>, feat_bytes, &optin) != cudaSuccess) return;   // surfaces as the launch error
     if (g.n_chunks > 1) {
         {
             ProfScope ps(kProfIirState, st);
@@ -430,21 +427,18 @@ static void run_pieces(const TIn* x, double* feat, double* init_state, double* s
     SGS_LAUNCHED();
     constexpr int hand_bytes = kPipes * (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
     constexpr int feat_bytes = hand_bytes + kPipes * RING * 32 * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_iir_pieces<NB, MONIC, kModeFeat, RING, kPipes, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, feat_bytes);
-        cudaFuncSetAttribute(k_iir_pieces<NB, MONIC, kModeState, RING, kPipes, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, hand_bytes);
-        attr_set = true;
-    }
+    static unsigned long long optin_f = 0, optin_s = 0;
+    if (smem_optin(k_iir_pieces<NB, MONIC, kModeFeat, RING, kPipes, TIn>, feat_bytes, &optin_f) != cudaSuccess ||
+        smem_optin(k_iir_pieces<NB, MONIC, kModeState, RING, kPipes, TIn>, hand_bytes, &optin_s) != cudaSuccess) return;   // surfaces as the launch error
     const int grid = ceil_div(n_pieces, kPipes);
     {
-        ProfScope ps(kProfIirState, st);
+        ProfScope ps(kProfPiecesState, st);
         k_iir_pieces<NB, MONIC, kModeState, RING, kPipes, TIn><<<grid, kPipes * kStages * 32, hand_bytes, st>>>(
             x, feat, init_state, seg_state, segs, piece_first, n_pieces, starts, zf, cf, g);
     }
     SGS_LAUNCHED();
     {
-        ProfScope ps(kProfIirFeat, st);
+        ProfScope ps(kProfPiecesFeat, st);
         k_iir_pieces<NB, MONIC, kModeFeat, RING, kPipes, TIn><<<grid, kPipes * kStages * 32, feat_bytes, st>>>(
             x, feat, init_state, seg_state, segs, piece_first, n_pieces, starts, zf, cf, g);
     }

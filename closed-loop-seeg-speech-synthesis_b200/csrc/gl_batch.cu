@@ -178,8 +178,8 @@ int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int 
                  long long x_len, double* mx, short* pcm, cudaStream_t st) {
     const size_t smem = sizeof(double) * kN + sizeof(cplx) * (kM + kBinsB + 1) + sizeof(double) * kRingB * kN +
                         sizeof(cplx) * kBW * kM + sizeof(double) * kBW * 64;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_gl_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    static unsigned long long optin = 0;
+    SGS_CUDA(smem_optin(k_gl_batch, smem, &optin));
     {
         ProfScope ps(kProfGlBatch, st);
         k_gl_batch<<<n_utt, kBW * 32, smem, st>>>(logmel, x, tab, T, n_mels, iters, x_len);

@@ -311,8 +311,8 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
     // 8 warps x 2 CTAs per SM: 128 registers per thread and 113 KB of shared memory per CTA (16 resident warps = 32 blocks)
     constexpr int W = 8;
     const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kG8SLen + kG8BufCplx) + sizeof(double) * kEaTabLen + sizeof(G8WarpSmem) * W;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_gl_blocks8<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    static unsigned long long optin = 0;
+    SGS_CUDA(smem_optin(k_gl_blocks8<W, 2>, smem, &optin));
     const long long n_pairs = (n_items + 1) / 2, want = (n_pairs + W - 1) / W;
     const int grid = (int)(want < 148LL * 2 * 8 ? want : 148LL * 2 * 8);
     const G8Tables t8{tab.window, tab.tw_t, tab.tw_full, tab.inv_idx, tab.inv_w};

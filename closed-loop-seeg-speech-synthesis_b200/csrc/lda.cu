@@ -201,8 +201,8 @@ int lda_run(const double* feat, const double* Wt, const double* bias, const doub
         SGS_CUDA(cudaGetLastError());
         return SGS_OK;
     }
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_lda_decode<kMaxClasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    static unsigned long long optin = 0;
+    SGS_CUDA(smem_optin(k_lda_decode<kMaxClasses>, 200 * 1024, &optin));
     dim3 grid(ceil_div(g.n_rows, kLdaFrames), n_sessions);
     { ProfScope ps(kProfLda, st); k_lda_decode<kMaxClasses><<<grid, kLdaFrames * kLdaWarps, smem, st>>>(feat, Wt, bias, cls, select, medians, taps, labels, spec, smooth, g, list, list_count); }
     SGS_LAUNCHED();

@@ -288,17 +288,20 @@ int lda_tc_run(const double* feat, const float* Bmat, const double* Wt, const do
     double* xnorm2 = nullptr;
     SGS_CUDA(cudaMallocAsync((void**)&packed, (size_t)g.n_tiles * kTileBytes, st));
     SGS_CUDA(cudaMallocAsync((void**)&xnorm2, sizeof(double) * (size_t)g.n_tiles * kTcM, st));
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_lda_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem); attr = true; }
+    static unsigned long long optin = 0;
+    SGS_CUDA(smem_optin(k_lda_tc, kTcSmem, &optin));
     SGS_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * n_frames_total, st));
     SGS_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
     k_lda_tc_prep<<<ceil_div(3 * kTcN, 128), 128, 0, st>>>(chan_mean, feat_chan, Wt, bias0, slice_bins, g.n_features, centre, bias);
     SGS_LAUNCHED();
     const int per_slice = g.n_tiles < 49 ? g.n_tiles : 49;              // 3 x 49 = 147 persistent CTAs on 148 SMs
     {
-        ProfScope ps(kProfLdaTc, st);
+        ProfScope ps(kProfLdaPack, st);
         k_lda_pack<<<g.n_tiles, 512, 0, st>>>(feat, feat_chan, feat_back, centre, packed, xnorm2, g);
-        SGS_LAUNCHED();
+    }
+    SGS_LAUNCHED();
+    {
+        ProfScope ps(kProfLdaTc, st);
         k_lda_tc<<<dim3(per_slice, 3), kTcThreads, kTcSmem, st>>>(packed, xnorm2, Bmat, bias, cls, slice_bins, wnorm, labels, flags, g);
     }
     SGS_LAUNCHED();

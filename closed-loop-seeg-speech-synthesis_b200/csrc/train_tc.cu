@@ -321,8 +321,8 @@ int lda_stats_tc_run(const double* x, long long n, long long row_stride, const i
     SGS_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned long long) * kTrF, st));
     SGS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * kTrOH, st));
     SGS_CUDA(cudaMemsetAsync(onehot, 0, (size_t)n_groups * kTrLboO, st));       // columns past bins * classes stay zero
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_tc_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem); attr = true; }
+    static unsigned long long optin = 0;
+    SGS_CUDA(smem_optin(k_tc_stats, kTrSmem, &optin));
     int slices = (int)(n / 4096);
     slices = slices < 1 ? 1 : (slices > 592 ? 592 : slices);
     k_tc_absmax<<<slices, kTrF, 0, st>>>(x, select, xbar, n, row_stride, nf, amax);

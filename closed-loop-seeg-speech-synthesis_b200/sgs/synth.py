@@ -37,6 +37,45 @@ def seeg_session(session, n_channels, sr, duration_s, dtype=np.float32):
     return x.astype(dtype)
 
 
+def seeg_sessions_device(sessions, n_channels, sr, duration_s, device='cuda', out=None):
+    """(S x T x C) float32 torch tensor generated ON the device: the same signal model as seeg_session (same envelope knots,
+    phases and channel weights per session number; the two Gaussian components come from torch's generator seeded with
+    1000 + session, so the samples differ from the numpy ones while every statistic is the same).  Config-5 scale inputs
+    (161 GB for 256 sessions) cannot be generated on the host and uploaded; they are made per rank where they are used."""
+    import torch
+    sessions = list(sessions)
+    n = int(round(duration_s * sr))
+    if out is None:
+        out = torch.empty((len(sessions), n, n_channels), dtype=torch.float32, device=device)
+    dev = out.device
+    t = torch.arange(n, device=dev, dtype=torch.float64) / float(sr)
+    lines = (10.0 * torch.sin(2 * np.pi * 100.0 * t) + 5.0 * torch.sin(2 * np.pi * 150.0 * t)).to(torch.float32)[:, None]
+    tmp = torch.empty((n, n_channels), dtype=torch.float32, device=dev)
+    for i, session in enumerate(sessions):
+        rng = np.random.default_rng(1000 + session)
+        kt, kv = _envelope(np.random.default_rng(5000 + session), duration_s)
+        phase = torch.from_numpy(rng.uniform(0, 2 * np.pi, n_channels)).to(dev)[None, :]
+        weight = torch.from_numpy(rng.uniform(0.0, 1.0, n_channels)).to(dev, torch.float32)[None, :]
+        # envelope: linear interpolation between the 8 Hz knots (np.interp in seeg_session)
+        knot_hz = 1.0 / (kt[1] - kt[0])
+        pos = t * knot_hz
+        i0 = pos.floor().long().clamp_(0, len(kv) - 2)
+        kvd = torch.from_numpy(kv).to(dev)
+        frac = (pos - i0.to(torch.float64))
+        g = (kvd[i0] * (1.0 - frac) + kvd[i0 + 1] * frac).to(torch.float32)[:, None]
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1000 + session)
+        x = out[i]
+        x.normal_(0.0, 20.0, generator=gen)
+        x += (30.0 * torch.sin(2 * np.pi * 50.0 * t[:, None] + phase)).to(torch.float32)
+        x += lines
+        tmp.normal_(0.0, 60.0, generator=gen)
+        tmp *= g
+        tmp *= weight
+        x += tmp
+    return out
+
+
 def audio_session(session, duration_s, sr=16000):
     """Audio already at 16 kHz (the reference decimates 48 kHz by 3 before use, train.py:125).
     Includes the N(0, 1e-4) dither the reference adds at train.py:294."""

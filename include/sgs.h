@@ -36,8 +36,10 @@ int sgs_synchronize(void* stream);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long sgs_launch_count(void);
 /* Per-kernel-class device time, measured with CUDA events on the launching stream (bench.py's roofline leg).
- * Enable, run, then read: name in {iir_init, iir_state, iir_carry, iir_feat, stack, lda, gl_blocks, gl_ola, lowpass,
- * stream, gl_batch, logmel, train}. */
+ * Enable, run, then read: name in {iir_init, iir_state, iir_carry, iir_feat, iir_pieces_state, iir_pieces_feat, stack, lda,
+ * lda_pack, lda_tc, gl_blocks, gl_ola, lowpass, stream, gl_batch, logmel, train, train_tc}.  iir_state / iir_feat are the
+ * (stream group x time chunk) grid of the feature scan, iir_pieces_* its balanced-pieces form (large jobs): the launch count
+ * of a class tells which decomposition a call took. */
 int sgs_profile_enable(int on);
 int sgs_profile_read(const char* name, double* total_ms, unsigned long long* launches);
 
@@ -120,7 +122,9 @@ void sgs_lda_model_destroy(sgs_lda_model* model);
  * stacked view is assembled on the fly exactly as sgs_feat_stack would (first_row/order/step as there; pass
  * order = 0, first_row = 0 to decode already-stacked rows of width n_channels).
  * labels, spec: [n_sessions][n_rows][n_bins] fp64, either may be NULL.  smooth != 0 applies the taps across bins
- * with scipy's 'reflect' boundary. */
+ * with scipy's 'reflect' boundary.
+ * A model handle is SINGLE-STREAM: the call keeps per-call scratch (centring vector, re-score list, its counter) in the
+ * handle, so two decodes of one model must not be in flight on two streams at once - create one model per stream. */
 int sgs_lda_decode(const sgs_lda_model* model, const double* feat, int n_sessions, int n_windows, int n_channels,
                    int n_rows, int first_row, int order, int step, double* labels, double* spec, int smooth,
                    void* stream);

@@ -175,6 +175,49 @@ def gen_train_decode():
     print('offline_decoding.npz', spec.shape, audio.shape, rec.shape)
 
 
+def gen_model128():
+    """The decode model of the 128-channel configurations ("produced by train.train on 120 s of the same
+    generator"): the UNMODIFIED reference train.train on a 120 s x 128-channel @ 2048 Hz synthetic session, packed as dense
+    arrays (coef_/intercept_/classes_ per mel bin) so bench.py, smoke() and the full-size GPU tests decode with a TRAINED
+    model instead of random weights, plus the reference node chain's output on 2 s of a held-out session of the same shape."""
+    sr, n_ch, dur = 2048, 128, 120.0
+    eeg = synth.seeg_session(101, n_ch, sr, dur).astype(np.float64)
+    audio16 = synth.audio_session(101, dur)
+    ref_train.decimate = lambda a, q: a
+    x_train, q, medians, estimators, select = ref_train.train(eeg, audio16, sr, 48000, [])
+    W = np.zeros((40, 9, x_train.shape[1]))
+    B = np.full((40, 9), -np.inf)
+    CL = np.zeros((40, 9))
+    for i, e in enumerate(estimators):
+        k = len(e.classes_)
+        assert e.coef_.shape[0] == k, 'binary bin in the 128-channel model: pack it by hand'
+        W[i, :k], B[i, :k], CL[i, :k] = e.coef_, e.intercept_, e.classes_
+    out = dict(sr=sr, n_ch=n_ch, dur=dur, train_session=101, eeg_digest=digest(eeg), audio_digest=digest(audio16),
+               select=select.astype(np.int32), medians=medians, coef=W, intercept=B, classes=CL,
+               n_classes=np.array([len(e.classes_) for e in estimators]),
+               train_accuracy=np.array([np.mean(e.predict(x_train) == q[:len(x_train), i]) for i, e in enumerate(estimators)]))
+    # held-out 2 s through the reference node chain (decode.py wiring, 64-sample packets as decode.py:116 sets for 2048 Hz)
+    test = synth.seeg_session(102, n_ch, sr, 2.0).astype(np.float64)
+    src = Node.Node(name='src', has_inputs=False)
+    fe = ECogFeatCalc.ECogFeatCalc(sr, frame_len_ms=50, frame_shift_ms=10, model_order=4, step_size=5, chunk_size=64)(src)
+    lda = LDASynthesis.LDASynthesis(pickle.dumps(estimators), select=select)(fe)
+    deq = Dequantization.Dequantization(medians)(lda)
+    gl = GriffinLim.GriffinLimSynthesis(originalFrameSizeMs=16, frameShiftMs=10, sampleRate=16000, melCoeffCount=40,
+                                        numReconstructionIterations=8, normFactor=10)(deq)
+    r_lab, r_spec, r_audio = [], [], []
+    lda.add_output(lambda f: r_lab.append(np.array(f, copy=True)))
+    deq.add_output(lambda f: r_spec.append(np.array(f, copy=True)))
+    gl.add_output(lambda f: r_audio.append(np.array(f, copy=True)))
+    np.random.seed(4010)
+    for i in range(0, len(test), 64):
+        src.output_data(np.array(test[i:i + 64]))
+    out.update(test_session=102, test_digest=digest(test), dec_labels=np.array(r_lab).astype(np.int8), dec_spec=np.array(r_spec),
+               dec_audio=np.hstack([a for a in r_audio if len(a)]), dec_noise_seed=4010)
+    np.savez_compressed(os.path.join(OUT, 'model128.npz'), **out)
+    print('model128.npz', {k: getattr(v, 'shape', v) for k, v in out.items()})
+    print('train accuracy per bin (mean %.3f)' % out['train_accuracy'].mean())
+
+
 def gen_griffinlim():
     out = {}
     med = synth.default_medians()
@@ -210,9 +253,9 @@ def gen_griffinlim():
 
 
 if __name__ == '__main__':
-    gen_features()
-    gen_mel()
-    gen_griffinlim()
-    gen_train_decode()
+    only = sys.argv[1:]
+    for fn in (gen_features, gen_mel, gen_griffinlim, gen_train_decode, gen_model128):
+        if not only or fn.__name__ in only:
+            fn()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

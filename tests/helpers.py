@@ -28,3 +28,11 @@ def batch_noise(seed, n_frames, win=800, hop=160, n_bins=401):
     """np.random.rand(2*T*n_bins) of offline.griffin_lim (offline.py:164); only the head matters (R4)."""
     rs = np.random.RandomState(seed)
     return rs.rand(2 * n_frames * n_bins)[:hop * (n_frames - 1) + win]
+
+
+def model128():
+    """The reference-trained model of the 128-channel configurations (tests/golden/model128.npz, written by
+    oracle/gen_golden.py:gen_model128 from the unmodified reference's train.train on 120 s of sgs.synth session 101):
+    ((W, bias, classes), select, medians, fixture)."""
+    G = load('model128.npz')
+    return (G['coef'], G['intercept'], G['classes']), G['select'], G['medians'], G

@@ -10,7 +10,7 @@ import pytest
 
 import oracle as O
 from sgs import synth
-from helpers import load, digest, node_noise, batch_noise, GOLDEN
+from helpers import load, digest, node_noise, batch_noise, model128, GOLDEN
 
 
 @pytest.mark.parametrize('sr', [1024, 2048])
@@ -132,3 +132,23 @@ def test_pickled_reference_estimators_load():
     G = load('train_decode.npz')
     assert len(est) == 40
     assert np.array_equal(est[5].coef_, G['coef'][5, :est[5].coef_.shape[0]])
+
+
+def test_model128_streaming_decode_matches_reference():
+    """The 128-channel @ 2048 Hz model (reference train.train, 120 s) and the reference node chain's decode of a held-out 2 s
+    in 64-sample packets: the oracle's closed form reproduces labels, spectrogram and int16 audio bit for bit from the
+    packed coefficients - the model bench.py, smoke() and the full-size GPU tests decode with."""
+    (W, b, cls), select, medians, G = model128()
+    sr, n_ch = int(G['sr']), int(G['n_ch'])
+    assert (sr, n_ch) == (2048, 128) and W.shape == (40, 9, 150)
+    test = synth.seeg_session(int(G['test_session']), n_ch, sr, 2.0).astype(np.float64)
+    assert digest(test) == str(G['test_digest'])
+    x = O.ecog_feat_calc(test, sr, 50, 10, 4, 5, 50, 64)
+    lab, _ = O.lda_predict_packed(x, W, b, cls, select)
+    assert np.array_equal(lab, G['dec_labels'])
+    spec = O.dequantization_node(lab, medians)
+    assert np.array_equal(spec, G['dec_spec'])
+    pcm, _ = O.GriffinLimNode(16, 10, 16000, 40, 8, norm_factor=10).synthesize(spec, node_noise(int(G['dec_noise_seed']), len(spec)))
+    assert np.array_equal(pcm, G['dec_audio'])
+    # a trained model: not one class everywhere, and margins much tighter than random weights give
+    assert len(np.unique(lab)) >= 5 and G['n_classes'].max() == 9
