@@ -323,7 +323,7 @@ def run_ours(args):
             "ms_each_step": [round(v, 3) for v in step_ms],
             "host_enqueue_ms_each_step": [round(v * 1e3, 3) for v in host_t],
             "host_stage_ms_first_two_steps": stage_t[:6] or None,
-            "lda_frames_rescored_fp64": [rescored, S * n_frames],
+            "lda_frame_bins_rescored_fp64": [rescored, S * n_frames * 40],
             "model": "reference train.train on 120 s of the same generator (tests/golden/model128.npz)",
             "self_check": self_check,
             "clocks": sampler.summary() if sampler is not None else None,

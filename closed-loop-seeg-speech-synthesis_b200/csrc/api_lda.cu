@@ -114,8 +114,8 @@ int sgs_lda_model_create(sgs_lda_model** model, int n_bins, int n_classes, int n
         if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_centre, sizeof(double) * kTcK);
         if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_feat_chan, sizeof(int) * kTcK);
         if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_feat_back, sizeof(int) * kTcK);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_count, sizeof(int));
-        if (e == cudaSuccess) e = cudaMemset(m->d_count, 0, sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_count, 2 * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(m->d_count, 0, 2 * sizeof(int));
         m->tc_ok = (e == cudaSuccess);
     }
     if (e != cudaSuccess) { sgs_lda_model_destroy(m); return sgs::cuda_fail(e, "model upload", __FILE__, __LINE__); }
@@ -178,8 +178,9 @@ int sgs_lda_decode(const sgs_lda_model* cm, const double* feat, int n_sessions, 
         int *d_flags = nullptr, *d_list = nullptr, *d_count = m->d_count;
         bool own_lab = false;
         if (e == cudaSuccess && !d_lab) { e = cudaMallocAsync((void**)&d_lab, out_bytes, st); own_lab = true; }
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_flags, sizeof(int) * n_frames, st);
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_list, sizeof(int) * n_frames, st);
+        // one bin mask per (frame, slice of <= 14 bins); the list holds the non-zero ones
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_flags, sizeof(int) * 3 * n_frames, st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_list, sizeof(int) * 3 * n_frames, st);
         if (e != cudaSuccess) rc = cuda_fail(e, "tensor-core scratch", __FILE__, __LINE__);
         if (rc == SGS_OK)
             rc = col_means_run((const double*)sf.dev, (long long)n_sessions * n_windows, n_channels, m->d_iota, n_channels, m->d_chan_mean, st);
@@ -192,8 +193,8 @@ int sgs_lda_decode(const sgs_lda_model* cm, const double* feat, int n_sessions, 
                             m->d_feat_back, m->d_centre, m->d_slice_bins, m->d_wnorm, d_lab, d_flags, d_list, d_count, n_frames, tg, st);
         }
         if (rc == SGS_OK)
-            rc = lda_run((const double*)sf.dev, m->d_Wt, m->d_bias, m->d_cls, m->d_select, m->d_medians, m->d_taps, d_lab, nullptr, 0,
-                         n_sessions, g, st, d_list, d_count, n_frames);
+            rc = lda_pairs_run((const double*)sf.dev, m->d_Wt, m->d_bias, m->d_cls, m->d_select, d_lab, g, st, d_flags, d_list, d_count,
+                               m->d_slice_bins, 3 * n_frames);
         if (rc == SGS_OK && spec)
             rc = dequantize_run(d_lab, m->d_medians, m->d_taps, m->smooth_radius, smooth, m->n_bins, m->n_levels, n_frames, (double*)ss.dev, st);
         if (own_lab && d_lab) cudaFreeAsync(d_lab, st);
@@ -237,7 +238,7 @@ int sgs_lda_last_rescored(const sgs_lda_model* m, int* n_frames) {
     *n_frames = 0;
     if (!m->d_count) return SGS_OK;
     SGS_CUDA(cudaDeviceSynchronize());
-    SGS_CUDA(cudaMemcpy(n_frames, m->d_count, sizeof(int), cudaMemcpyDeviceToHost));
+    SGS_CUDA(cudaMemcpy(n_frames, m->d_count + 1, sizeof(int), cudaMemcpyDeviceToHost));
     return SGS_OK;
 }
 

@@ -47,6 +47,9 @@ struct LdaGeom {
 int lda_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select,
             const double* medians, const double* taps, double* labels, double* spec, int smooth, int n_sessions,
             const LdaGeom& g, cudaStream_t st, const int* list, const int* list_count, long long list_cap);
+int lda_pairs_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select, double* labels,
+                  const LdaGeom& g, cudaStream_t st, const int* flags, const int* list, const int* list_count, const int* slice_bins,
+                  long long list_cap);
 struct LdaTcGeom {
     int n_windows, n_channels, n_rows, first_row, order, step, n_bins, n_features;
     int tiles_per_session, n_tiles;

@@ -180,6 +180,86 @@ k_lda_rows(const double* __restrict__ feat, const double* __restrict__ Wt, const
     }
 }
 
+// ---- exact re-scoring of the (frame, bin) pairs the tensor-core filter could not decide (lda_tc.cu) -----------------------------
+// list[e] = frame * 3 + slice of a flagged entry, flags[list[e]] = bit mask of its undecided bins (relative to the slice's
+// first bin).  One warp per entry: the frame's selected, stacked features are gathered once into shared memory; lanes
+// (p, k) = (lane / 9, lane % 9), p < 3, score class k of the p-th undecided bin with the arithmetic of k_lda_decode -
+// acc = fma(x_f, W[b][f][k], acc) for f ascending, then + bias, strict argmax in class order - so the label equals the
+// fp64 kernel's to the bit.
+constexpr int kPairWarps = 8;
+template <int KC>
+__global__ void __launch_bounds__(kPairWarps * 32)
+k_lda_pairs(const double* __restrict__ feat, const double* __restrict__ Wt, const double* __restrict__ bias,
+            const double* __restrict__ cls, const int* __restrict__ select, double* __restrict__ labels, const LdaGeom g,
+            const int* __restrict__ flags, const int* __restrict__ list, const int* __restrict__ list_count,
+            const int* __restrict__ slice_bins) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* xs = sm + (size_t)warp * g.n_features;
+    const int n_list = *list_count;
+    const int p = lane / KC, k = lane - p * KC;
+    for (int e = blockIdx.x * kPairWarps + warp; e < n_list; e += gridDim.x * kPairWarps) {
+        const int entry = list[e];
+        const int frame = entry / 3, slice = entry - 3 * frame;
+        unsigned mask = (unsigned)flags[entry];
+        const int bin0 = slice_bins[slice];
+        const int sess = frame / g.n_rows, row = frame - sess * g.n_rows;
+        const double* fs = feat + (long long)sess * g.n_windows * g.n_channels;
+        for (int f = lane; f < g.n_features; f += 32) {
+            const int col = select[f];
+            const int c = col / (g.order + 1), tap = col - c * (g.order + 1);
+            const int w = row + g.first_row - (g.order - tap) * g.step;
+            xs[f] = (w >= 0) ? fs[(long long)w * g.n_channels + c] : 0.0;
+        }
+        __syncwarp();
+        while (mask) {
+            int myb = -1;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (mask) {
+                    const int bb = __ffs(mask) - 1;
+                    if (q == p) myb = bb;
+                    mask &= mask - 1;
+                }
+            }
+            const bool active = myb >= 0;                                // p == 3 (lanes 27-31) never matches
+            const int b = bin0 + (active ? myb : 0);
+            double s = -INFINITY;
+            if (active) {
+                const double* wb = Wt + (long long)b * g.n_features * KC + k;
+                double acc = 0.0;
+#pragma unroll 10
+                for (int f = 0; f < g.n_features; ++f) acc = fma(xs[f], __ldg(wb + f * KC), acc);
+                s = acc + bias[b * KC + k];
+            }
+            const int base = p < 3 ? p * KC : 0;
+            int best = 0;
+            double bv = __shfl_sync(0xffffffffu, s, base);
+#pragma unroll
+            for (int j = 1; j < KC; ++j) {
+                const double sj = __shfl_sync(0xffffffffu, s, base + j);
+                if (sj > bv) { bv = sj; best = j; }                      // strict: the first maximum wins, as numpy argmax
+            }
+            if (active && k == 0) labels[(long long)frame * g.n_bins + b] = cls[b * KC + best];
+        }
+        __syncwarp();                                                    // xs is reused by the next entry
+    }
+}
+
+int lda_pairs_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select, double* labels,
+                  const LdaGeom& g, cudaStream_t st, const int* flags, const int* list, const int* list_count, const int* slice_bins,
+                  long long list_cap) {
+    if (g.n_classes != kMaxClasses) { set_error("LDA kernel is built for %d classes per bin (got %d)", kMaxClasses, g.n_classes); return SGS_ERR_UNSUPPORTED; }
+    const size_t smem = sizeof(double) * kPairWarps * (size_t)g.n_features;
+    if (smem > 48 * 1024) { set_error("too many features (%d) for the pair re-scoring kernel", g.n_features); return SGS_ERR_UNSUPPORTED; }
+    const long long want = (list_cap + kPairWarps - 1) / kPairWarps;
+    const int grid = (int)std::min<long long>(std::max<long long>(want, 1), 148 * 8);
+    { ProfScope ps(kProfLda, st); k_lda_pairs<kMaxClasses><<<grid, kPairWarps * 32, smem, st>>>(feat, Wt, bias, cls, select, labels, g, flags, list, list_count, slice_bins); }
+    SGS_LAUNCHED();
+    SGS_CUDA(cudaGetLastError());
+    return SGS_OK;
+}
+
 constexpr long long kLdaRowsMax = 256;      // up to this many frames the per-frame kernel has the lower latency
 
 int lda_run(const double* feat, const double* Wt, const double* bias, const double* cls, const int* select,

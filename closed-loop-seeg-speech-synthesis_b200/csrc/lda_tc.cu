@@ -6,8 +6,10 @@
 // x' = x_hi + x_lo, W' = W_hi + W_lo (each part a properly rounded tf32), accumulated as hi.hi + hi.lo + lo.hi in the
 // fp32 TMEM accumulator (24 bits of each operand).  That is a FILTER, not the answer: the epilogue takes the per-bin
 // argmax and flags every frame in which the best and second-best class of some bin are closer than a bound on the
-// tensor-core error; flagged frames are re-scored exactly by the fp64 kernel (lda.cu).  Class indices therefore equal
-// the fp64 result everywhere (LDASynthesis.py:25-26 semantics), not just "up to near-ties".
+// tensor-core error; the flagged (frame, bin) pairs - a bit mask per frame and slice - are re-scored exactly in fp64
+// (lda.cu:k_lda_pairs).  Class indices therefore equal the fp64 result everywhere (LDASynthesis.py:25-26 semantics), not
+// just "up to near-ties".  With a TRAINED model 13 % of the frames have a near-tie in some bin (random weights: 0.003 %),
+// but only ~1 of their 40 bins: re-scoring pairs instead of whole frames is what keeps the exact pass off the step time.
 //
 // k_lda_pack  full-occupancy pre-pass: gathers the stacked, selected features of every 128-frame tile straight from
 //             the un-stacked log-power array, centres them, splits hi/lo and writes them to HBM already in the
@@ -215,7 +217,7 @@ k_lda_tc(const float* __restrict__ packed, const double* __restrict__ xnorm2, co
             const double* cls_s = cls + slice * kTcN;
             mbar_wait(bar_acc_full + 8 * buf, (t_local >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            bool tie = false;
+            unsigned tiemask = 0;                                       // bins of this slice whose argmax the filter cannot decide
             float best = -INFINITY, second = -INFINITY;
             int best_k = 0;
 #pragma unroll
@@ -237,7 +239,7 @@ k_lda_tc(const float* __restrict__ packed, const double* __restrict__ xnorm2, co
                                 // |fp32 score - exact| <= eps |x'| |w| (tensor-core split) + rounding of the bias and of the fp32 add
                                 const float fin2 = second > -INFINITY ? fabsf(second) : 0.0f;
                                 const float thr = fmaf(margin0, s_wnf[bin], s_tol[bin]) + 4.8e-7f * (fabsf(best) + fin2);
-                                if (best - second < thr) tie = true;
+                                if (best - second < thr) tiemask |= 1u << bin;
                                 if (elive) lab_row[bin] = cls_s[bin * kTcClasses + best_k];
                             }
                             best = -INFINITY; second = -INFINITY; best_k = 0;
@@ -247,7 +249,7 @@ k_lda_tc(const float* __restrict__ packed, const double* __restrict__ xnorm2, co
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(bar_acc_empty + 8 * buf);                       // 128 arrivals free the accumulator
-            if (elive && tie) flags[(long long)sess * g.n_rows + erow] = 1;
+            if (elive && tiemask) flags[((long long)sess * g.n_rows + erow) * 3 + slice] = (int)tiemask;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -275,10 +277,14 @@ __global__ void k_lda_tc_prep(const double* __restrict__ chan_mean, const int* _
     }
 }
 
-// compact the flagged frames into a list (order does not matter)
+// compact the flagged (frame, slice) entries into a list (order does not matter); count[0] = entries, count[1] = flagged (frame, bin) pairs
 __global__ void k_flag_list(const int* __restrict__ flags, long long n, int* __restrict__ list, int* __restrict__ count) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flags[i]) list[atomicAdd(count, 1)] = (int)i;
+    const int m = i < n ? flags[i] : 0;
+    if (m) {
+        list[atomicAdd(count, 1)] = (int)i;
+        atomicAdd(count + 1, __popc((unsigned)m));
+    }
 }
 
 int lda_tc_run(const double* feat, const float* Bmat, const double* Wt, const double* bias0, const double* chan_mean, double* bias,
@@ -290,8 +296,8 @@ int lda_tc_run(const double* feat, const float* Bmat, const double* Wt, const do
     SGS_CUDA(cudaMallocAsync((void**)&xnorm2, sizeof(double) * (size_t)g.n_tiles * kTcM, st));
     static unsigned long long optin = 0;
     SGS_CUDA(smem_optin(k_lda_tc, kTcSmem, &optin));
-    SGS_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * n_frames_total, st));
-    SGS_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+    SGS_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 3 * n_frames_total, st));
+    SGS_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int), st));
     k_lda_tc_prep<<<ceil_div(3 * kTcN, 128), 128, 0, st>>>(chan_mean, feat_chan, Wt, bias0, slice_bins, g.n_features, centre, bias);
     SGS_LAUNCHED();
     const int per_slice = g.n_tiles < 49 ? g.n_tiles : 49;              // 3 x 49 = 147 persistent CTAs on 148 SMs
@@ -307,7 +313,7 @@ int lda_tc_run(const double* feat, const float* Bmat, const double* Wt, const do
     SGS_LAUNCHED();
     cudaFreeAsync(packed, st);
     cudaFreeAsync(xnorm2, st);
-    k_flag_list<<<ceil_div(n_frames_total, 256), 256, 0, st>>>(flags, n_frames_total, list, count);
+    k_flag_list<<<ceil_div(3 * n_frames_total, 256), 256, 0, st>>>(flags, 3 * n_frames_total, list, count);
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());
     return SGS_OK;

@@ -16,6 +16,7 @@ from sgs.features import FeatureExtractor
 
 logger = logging.getLogger('ECoGFeatCalc.py')
 MAX_PUSH = 128      # samples per device push (csrc/stream.cu)
+MAX_FRAMES = 16     # frames one device push can complete (csrc/kernels.cuh:kMaxFramesPerPush)
 
 
 class ECogFeatCalc(Node.Node):
@@ -87,18 +88,30 @@ class ECogFeatCalc(Node.Node):
         except Exception:
             pass
 
-    def _schedule(self, n_new):
-        """Frames whose end falls inside the next n_new samples (FrameBuffer.py:147-177)."""
+    def _end_of_frame(self, k):
+        """End (exclusive, zero-fill-prefixed coordinates) of frame k - FrameBuffer.py:35,177, Python's banker's round."""
+        return round(((self._first_ms + k * float(self.frame_shift_ms)) / 1000.0) * float(self.sample_rate))
+
+    def _schedule(self, n_max):
+        """(n, ends, idx): how many of the next n_max samples go into this push, and the frames whose end falls inside them
+        (FrameBuffer.py:147-177).  A device push completes at most MAX_FRAMES frames: when more would end inside n_max samples
+        (sample rates below ~800 Hz at a 10 ms shift, or a short frame_shift_ms) the push is cut just before the end of the
+        first frame that does not fit, so no frame is ever deferred past the samples that complete it."""
         plan = self._fe.plan
-        total = plan.zero_fill + self._consumed + n_new
-        ends, idx = [], []
-        while self._next_end <= total and len(ends) < 16:
+        base = plan.zero_fill + self._consumed
+        n, ends, idx = n_max, [], []
+        while self._next_end <= base + n:
+            if len(ends) == MAX_FRAMES:
+                n = self._next_end - 1 - base
+                break
             ends.append(self._next_end - plan.zero_fill)
             idx.append(self._frame_count)
             self._frame_count += 1
-            self._next_end = round(((self._first_ms + self._frame_count * float(self.frame_shift_ms)) / 1000.0)
-                                   * float(self.sample_rate))
-        return ends, idx
+            self._next_end = self._end_of_frame(self._frame_count)
+        if n < 1 or (ends and ends[-1] + plan.zero_fill > base + n):
+            raise ValueError("frame_shift_ms=%r at sample_rate=%r completes more than %d frames per sample: unsupported"
+                             % (self.frame_shift_ms, self.sample_rate, MAX_FRAMES))
+        return n, ends, idx
 
     def add_data(self, data, data_id=None):
         data = np.asarray(data)
@@ -114,9 +127,7 @@ class ECogFeatCalc(Node.Node):
         self._pending = data[usable:].copy() if usable < len(data) else None
         pos = 0
         while pos < usable:
-            n = min(MAX_PUSH, usable - pos)
-            # keep at most 16 frames per push: shrink the push if a long chunk would complete more
-            ends, idx = self._schedule(n)
+            n, ends, idx = self._schedule(min(MAX_PUSH, usable - pos))
             block = np.ascontiguousarray(data[pos:pos + n])
             e = np.asarray(ends, dtype=np.int64)
             k = np.asarray(idx, dtype=np.int64)

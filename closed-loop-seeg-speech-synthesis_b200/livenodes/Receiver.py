@@ -13,10 +13,45 @@ import multiprocessing
 import multiprocessing.util
 import os
 import queue
+import signal
 import threading
 import time
 
 from . import Node
+
+# Receivers that hold frames in THIS process, and the SIGTERM hook that hands those frames over before a terminated feeder
+# dies: Sender.stop_processing (like the reference's, Sender.py:69-70) ends the feeder with Process.terminate(); SIGTERM
+# skips multiprocessing's finalizers, so without the hook up to flush_interval of frames would never reach the Manager
+# list, while the reference, appending frame by frame, loses nothing.
+_live = {'pid': None, 'receivers': [], 'previous': None}
+
+
+def _on_sigterm(signum, frame):
+    for r in list(_live['receivers']):
+        try:
+            r.flush()
+        except Exception:
+            pass
+    prev = _live['previous']
+    if callable(prev):
+        prev(signum, frame)
+        return
+    signal.signal(signal.SIGTERM, signal.SIG_DFL)
+    os.kill(os.getpid(), signal.SIGTERM)
+
+
+def _register(receiver):
+    pid = os.getpid()
+    if _live['pid'] != pid:
+        _live.update(pid=pid, receivers=[], previous=None)
+        # only a forked feeder is ended by terminate(); the collecting parent flushes in get_data / stop_processing
+        if multiprocessing.parent_process() is not None and threading.current_thread() is threading.main_thread():
+            try:
+                prev = signal.signal(signal.SIGTERM, _on_sigterm)
+                _live['previous'] = prev if prev not in (signal.SIG_DFL, signal.SIG_IGN, None, _on_sigterm) else None
+            except (ValueError, OSError):
+                pass
+    _live['receivers'].append(receiver)
 
 
 class Receiver(Node.Node):
@@ -43,14 +78,19 @@ class Receiver(Node.Node):
         self._thread = None
         self._unsent = []
         multiprocessing.util.Finalize(self, self.flush, exitpriority=100)
+        _register(self)
 
     def _flusher(self, q):
         while True:
             batch = q.get()
             try:
-                self.data.extend(batch)
-            except Exception:                # keep the frames; the next synchronous flush retries and reports
+                # batches that failed earlier go first, so that frames reach the list in the order they were produced
                 self._unsent.append(batch)
+                while self._unsent:
+                    self.data.extend(self._unsent[0])
+                    self._unsent.pop(0)
+            except Exception:                # keep the frames, in order; the next hand-over (or synchronous flush) retries
+                pass
             finally:
                 q.task_done()
 

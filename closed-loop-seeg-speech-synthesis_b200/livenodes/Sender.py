@@ -56,4 +56,6 @@ class Sender(Node.Node):
         super().stop_processing(recurse)
         if self.feeder_process is not None:
             self.feeder_process.terminate()
+            # the feeder's receivers hand their last batch over on SIGTERM (Receiver.py): wait for that before the caller reads them
+            self.feeder_process.join(5.0)
         self.feeder_process = None

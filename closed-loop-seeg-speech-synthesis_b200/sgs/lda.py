@@ -72,7 +72,7 @@ class LdaDecoder:
             pass
 
     def last_rescored(self):
-        """Frames the last tensor-core decode re-scored exactly in fp64 (0 when the fp64 kernel ran alone)."""
+        """(frame, bin) pairs the last tensor-core decode re-scored exactly in fp64 (0 when the fp64 kernel ran alone)."""
         n = _lib.c_int(0)
         _lib.check(_lib.lib().sgs_lda_last_rescored(self.handle(), _lib.C.byref(n)))
         return n.value

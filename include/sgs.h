@@ -129,9 +129,9 @@ int sgs_lda_decode(const sgs_lda_model* model, const double* feat, int n_session
                    int n_rows, int first_row, int order, int step, double* labels, double* spec, int smooth,
                    void* stream);
 /* For batches of >= 4096 frames sgs_lda_decode scores on the tensor cores (split-TF32 tcgen05 GEMM) and re-scores in
- * fp64 every frame whose top-two gap in some bin is below the tensor-core error bound; this returns how many frames the
- * last such call re-scored.  SGS_LDA_TC=0 in the environment forces the pure fp64 kernel. */
-int sgs_lda_last_rescored(const sgs_lda_model* model, int* n_frames);
+ * fp64 every (frame, bin) whose top-two gap is below the tensor-core error bound; this returns how many (frame, bin)
+ * pairs - of frames x n_bins - the last such call re-scored.  SGS_LDA_TC=0 in the environment forces the pure fp64 kernel. */
+int sgs_lda_last_rescored(const sgs_lda_model* model, int* n_pairs);
 
 /* ---------------------------------------------------------------------------------------------------
  * Griffin-Lim, streaming-node semantics (livenodes/GriffinLim.py:13-174), batched over frames and sessions.

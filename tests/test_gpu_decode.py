@@ -142,7 +142,7 @@ def test_lda_tensor_core_path_equals_fp64(model, monkeypatch):
     want = O.lda_predict(fe.stack(lp[1], online=True), est, G['select'])
     assert np.array_equal(lab_tc[1], want)
     assert 0 <= rescored < 0.25 * lab_tc.shape[0] * lab_tc.shape[1], rescored       # the filter has to actually filter
-    print('tensor-core LDA: %d of %d frames re-scored in fp64' % (rescored, lab_tc.shape[0] * lab_tc.shape[1]))
+    print('tensor-core LDA: %d of %d (frame, bin) pairs re-scored in fp64' % (rescored, lab_tc.shape[0] * lab_tc.shape[1] * 40))
     # offline view (first_row = 20) on device-resident input
     import torch
     lpo = fe.log_power(torch.from_numpy(xs).cuda())

@@ -279,3 +279,72 @@ def test_gl_write_head_table_equals_the_node_loop():
                 want[k] = int((ms / 1000.0) * op.plan.sample_rate)
             assert np.array_equal(got, want)
             assert op.positions(70000, start) is got and not got.flags.writeable       # cached, shared, read-only
+
+
+def test_receiver_keeps_the_tail_when_the_feeder_is_terminated():
+    """Sender.stop_processing ends its feeder with Process.terminate() (reference Sender.py:64-70): SIGTERM skips the exit
+    finalizers, so the batching Receiver hands its frames over from a SIGTERM hook - like the reference's per-frame append
+    (flush_interval=0, attached next to it) nothing the feeder produced is lost, and the order is kept."""
+    from livenodes import Receiver, Sender
+    data = np.arange(4000, dtype=np.float64)[:, None]
+    snd = Sender.Sender(data, 1000, 2, asap=False)                       # 2-sample frames every 2 ms: runs for 4 s if not stopped
+    batched = Receiver.Receiver(flush_interval=3600.0)(snd)             # would only ever flush at exit
+    timed = Receiver.Receiver(flush_interval=0.25)(snd)
+    eager = Receiver.Receiver(flush_interval=0)(snd)                    # the reference's behaviour
+    snd.start_processing()
+    time.sleep(0.7)
+    snd.stop_processing()
+    a, b, c = batched.get_data(), timed.get_data(), eager.get_data()
+    assert len(c) > 100                                                 # the feeder did run
+    # the signal lands between two receivers' callbacks at worst: lengths differ by at most the frame in flight
+    assert abs(len(a) - len(c)) <= 1 and abs(len(b) - len(c)) <= 1, (len(a), len(b), len(c))
+    for got in (a, b):
+        first = np.array([f[0, 0] for f in got])
+        assert np.array_equal(first, 2.0 * np.arange(len(got)))         # complete and in order
+
+
+def test_receiver_resends_failed_batches_in_order():
+    from livenodes import Receiver
+
+    class Flaky(list):
+        fail = 2
+
+        def extend(self, batch):
+            if Flaky.fail > 0:
+                Flaky.fail -= 1
+                raise ConnectionError('manager away')
+            list.extend(self, batch)
+
+    rec = Receiver.Receiver(flush_interval=0.01)
+    rec.data = Flaky()
+    for i in range(40):
+        rec.add_data(i)
+        time.sleep(0.002)
+    rec.flush()
+    assert list(rec.data) == list(range(40))
+
+
+@pytest.mark.parametrize('sr,shift_ms', [(2048, 10), (512, 10), (2048, 0.5), (1024, 1), (600, 2.5)])
+def test_feature_node_schedule_never_defers_a_frame(sr, shift_ms):
+    """ECogFeatCalc._schedule (host side of the streaming push): every frame is scheduled in the push whose samples complete
+    it, at most 16 per push - pushes are cut short when more would end inside 128 samples - and the ends follow
+    FrameBuffer.py:35,177 exactly.  No device needed."""
+    from livenodes import ECogFeatCalc
+    node = ECogFeatCalc.ECogFeatCalc(sr, 50, shift_ms, has_inputs=False)
+    plan = node._fe.plan
+    first_ms = (float(plan.frame_size) / float(sr)) * 1000.0
+    want = lambda k: round(((first_ms + k * float(shift_ms)) / 1000.0) * float(sr)) - plan.zero_fill
+    total, k = 0, 0
+    left = 5000
+    while left > 0:
+        n, ends, idx = node._schedule(min(128, left))
+        assert 1 <= n <= 128 and len(ends) <= 16
+        for e, i in zip(ends, idx):
+            assert i == k and e == want(k)
+            assert total < e <= total + n or (k == 0 and e <= total + n)          # ends inside this push's samples
+            k += 1
+        assert want(k) > total + n                                               # the next frame is not complete yet
+        node._consumed += n
+        total += n
+        left -= n
+    assert k > 5000 * 1000.0 / sr / shift_ms - 10
