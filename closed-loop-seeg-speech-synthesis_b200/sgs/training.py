@@ -136,6 +136,225 @@ def distributed_lda_stats(x_local, select, labels_local, n_classes=9, group=None
     return allreduce_stats(lda_stats(x_local, select, labels_local, n_classes, xbar), group)
 
 
+# ---- train.train as a multi-GPU job (SURVEY.md 8e) ---------------------------------------------------------------------
+# One process per GPU under torch.distributed, every rank calling train.train with the same host arrays:
+#   * features + Spearman are sharded by CHANNEL BLOCK (channels are independent through filtering and windowing, and a
+#     rank correlation needs a column's whole time axis): rank r uploads and filters only its channels - the upload of the
+#     recording, the largest single cost of a 1 h session, shrinks by the world size;
+#   * the audio side (decimation, log-mel target, logistic borders, labels) is replicated: the Spearman target (the frame
+#     mean of the log-mel spectrogram) is needed whole on every rank, so there is no min/max exchange to make;
+#   * the per-column correlations are all-gathered (5 doubles per channel) and every rank derives the same `select`;
+#   * the selected columns, spread over the ranks that own their channels, are summed into one (N x 150) matrix - each column
+#     is non-zero on exactly one rank, so the sum is exact;
+#   * the LDA statistics are sharded by ROW: mean all-reduce, then ONE all-reduce of (n, G, class sums, counts);
+#   * the 40 eigen-problems are dealt round-robin and the fitted estimators all-gathered.
+# The orchestration takes its array operators as an object so that the CPU tests can drive it with numpy restatements over
+# gloo (tests/test_train_host.py); DeviceOps below is the product binding.
+
+def _dist(group=None):
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(group), dist.get_world_size(group)
+    except ImportError:
+        pass
+    return None, 0, 1
+
+
+def block_shard(n, rank, world):
+    """[lo, hi) of a contiguous balanced split of n items (sizes differ by at most one) - decode.session_shard's rule."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _allreduce_sum_(a, group=None):
+    """In-place sum over the group of a numpy array or torch tensor; returns (bytes, seconds) of the collective."""
+    import time
+    dist, _, world = _dist(group)
+    if world == 1:
+        return 0, 0.0
+    import torch
+    t = a if _lib._is_torch(a) else torch.from_numpy(a)
+    on_gpu = dist.get_backend(group) == 'nccl'
+    buf = t.cuda() if on_gpu and not t.is_cuda else t
+    if buf.is_cuda:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    if buf.is_cuda:
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if buf is not t:
+        t.copy_(buf)
+    return int(t.numel() * t.element_size()), dt
+
+
+def _allgather_objects(obj, group=None):
+    dist, _, world = _dist(group)
+    if world == 1:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+class DeviceOps:
+    """The device operators train.train is made of (libsgs through local/offline.py, sgs/spectrogram.py and this module)."""
+
+    def upload(self, a, dtype=None):
+        import torch
+        a = np.ascontiguousarray(a) if dtype is None else np.ascontiguousarray(a, dtype=dtype)
+        return torch.from_numpy(a).to(torch.device('cuda', torch.cuda.current_device()))
+
+    def sync(self):
+        import torch
+        torch.cuda.synchronize()
+
+    def features(self, eeg, sfreq_eeg):
+        from local.offline import herff2016_b
+        return herff2016_b(eeg, sfreq_eeg, 0.05, 0.01)
+
+    def target(self, audio, audio_sr):
+        from local.offline import compute_spectrogram
+        if audio_sr != 16000:
+            from .spectrogram import decimate
+            audio = decimate(audio, int(round(audio_sr / 16000)))
+        return compute_spectrogram(audio, 16000, 0.016, 0.01)
+
+    def quantization(self, y, nb_intervals):
+        return quantization(y, nb_intervals)
+
+    def spearman(self, x, y):
+        return spearman(x, y)
+
+    def zeros(self, shape, like):
+        import torch
+        return torch.zeros(shape, dtype=torch.float64, device=like.device)
+
+    def index(self, idx, like):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(like.device)
+
+    def contiguous(self, a):
+        return a.contiguous()
+
+    def to_host(self, a):
+        return a.cpu().numpy()
+
+    def col_means(self, x, select):
+        return col_means(x, select)
+
+    def lda_stats(self, x, select, labels, n_classes, xbar):
+        return lda_stats(x, select, labels, n_classes, xbar)
+
+
+last_profile = {}       # stage times / collective sizes of the last sharded_fit in this process (bench.py's config3 record)
+
+
+def sharded_fit(eeg, audio, sfreq_eeg, sfreq_audio, nb_mel_bins=40, nb_intervals=9, nb_feats=150, ops=None, group=None):
+    """train.py:132-168 after the bad-channel mask, on `world` ranks (see the block comment above; world = 1 is the
+    single-GPU path).  eeg (T x C) and audio are HOST arrays, the same on every rank.
+    Returns (x_train[:, select] (device / ops array), labels, medians, estimators, select)."""
+    import time
+    ops = ops or DeviceOps()
+    dist, rank, world = _dist(group)
+    prof = {'world': world}
+    t_all = time.perf_counter()
+
+    def lap(key, t0):
+        ops.sync()
+        prof[key] = prof.get(key, 0.0) + (time.perf_counter() - t0)
+
+    C = eeg.shape[1]
+    c0, c1 = block_shard(C, rank, world)
+    t0 = time.perf_counter()
+    eeg_d = ops.upload(eeg[:, c0:c1])
+    audio_d = ops.upload(audio, np.float64)
+    prof['h2d_bytes'] = int(eeg[:, c0:c1].nbytes + np.asarray(audio).size * 8)
+    lap('h2d_s', t0)
+
+    t0 = time.perf_counter()
+    x_r = ops.features(eeg_d, sfreq_eeg) if c1 > c0 else None          # (N x 5 (c1 - c0)), column (c - c0) * 5 + tap
+    del eeg_d
+    lap('features_s', t0)
+    t0 = time.perf_counter()
+    y = ops.target(audio_d, sfreq_audio)
+    del audio_d
+    y = y[20:-4]          # align the audio frames with the 20-frame context / 50 ms window of the features (train.py:144)
+    medians, borders, q = ops.quantization(y, nb_intervals)
+    lap('target_quantization_s', t0)
+
+    t0 = time.perf_counter()
+    if x_r is not None:
+        if len(x_r) != len(y):
+            # scipy.stats.spearmanr raises on unequal lengths; keep the reference's failure mode
+            raise ValueError("all the input array dimensions must match: %d feature rows vs %d target rows" % (len(x_r), len(y)))
+        rho_r, colsum_r = ops.spearman(x_r, y)
+    else:
+        rho_r, colsum_r = np.empty(0), np.empty(0)
+    lap('spearman_s', t0)
+    t0 = time.perf_counter()
+    parts = _allgather_objects((np.asarray(rho_r), np.asarray(colsum_r)), group)
+    cs = np.concatenate([p[0] for p in parts])
+    colsum = np.concatenate([p[1] for p in parts])
+    prof['rho_allgather_bytes'] = int(16 * len(cs)) if world > 1 else 0
+    prof['rho_allgather_s'] = time.perf_counter() - t0
+    cs[np.isclose(colsum, 0)] = 0
+    select = np.argsort(np.abs(cs))[np.max([-nb_feats, -len(cs)]):]       # train.py:108: ascending |rho|, not index order
+
+    # the selected columns, each from the rank that owns its channel
+    t0 = time.perf_counter()
+    n_rows = len(y)
+    mine = np.nonzero((select >= 5 * c0) & (select < 5 * c1))[0]
+    if world == 1:
+        x_sel = ops.contiguous(x_r[:, ops.index(select, x_r)])
+    else:
+        x_sel = ops.zeros((n_rows, len(select)), like=y)
+        if len(mine):
+            x_sel[:, ops.index(mine, y)] = x_r[:, ops.index(select[mine] - 5 * c0, y)]
+    del x_r
+    lap('column_select_s', t0)
+    prof['columns_allreduce_bytes'], prof['columns_allreduce_s'] = _allreduce_sum_(x_sel, group)
+
+    minimum = min(len(x_sel), len(q))
+    x_sel, q = x_sel[0:minimum, :], q[0:minimum, :]
+    t0 = time.perf_counter()
+    lo, hi = block_shard(minimum, rank, world)
+    ident = np.arange(len(select))
+    xl, ql = ops.contiguous(x_sel[lo:hi]), ops.contiguous(q[lo:hi])
+    local_mean = ops.col_means(xl, ident) if hi > lo else np.zeros(len(select))
+    mean_buf = np.concatenate([[float(hi - lo)], local_mean * (hi - lo)])
+    b1, s1 = _allreduce_sum_(mean_buf, group)
+    xbar = mean_buf[1:] / mean_buf[0]
+    stats = ops.lda_stats(xl, ident, ql, nb_intervals, xbar)
+    flat = np.concatenate([[stats['n']], stats['G'].ravel(), stats['sums'].ravel(), stats['counts'].ravel()])
+    ops.sync()
+    b2, s2 = _allreduce_sum_(flat, group)
+    nf = len(select)
+    o = 1
+    stats['n'] = float(flat[0])
+    stats['G'] = flat[o:o + nf * nf].reshape(nf, nf); o += nf * nf
+    stats['sums'] = flat[o:o + stats['sums'].size].reshape(stats['sums'].shape); o += stats['sums'].size
+    stats['counts'] = flat[o:o + stats['counts'].size].reshape(stats['counts'].shape)
+    stats['xbar'] = xbar
+    prof['stats_allreduce_bytes'], prof['stats_allreduce_s'] = b1 + b2, s1 + s2
+    lap('lda_stats_s', t0)
+
+    t0 = time.perf_counter()
+    bins = list(range(rank, nb_mel_bins, world))
+    fitted = fit_from_stats(stats, bins=bins)
+    estimators = [None] * nb_mel_bins
+    for part_bins, part in _allgather_objects((bins, fitted), group):
+        for b, e in zip(part_bins, part):
+            estimators[b] = e
+    prof['eigen_solves_s'] = time.perf_counter() - t0
+    prof['total_s'] = time.perf_counter() - t_all
+    last_profile.clear()
+    last_profile.update(prof)
+    return x_sel, q, medians, estimators, select
+
+
 class PackedLDA:
     """Minimal estimator (coef_/intercept_/classes_/predict) used when scikit-learn is not importable."""
 
@@ -160,12 +379,13 @@ def _new_estimator():
         return PackedLDA()
 
 
-def fit_from_stats(stats, tol=TOL):
+def fit_from_stats(stats, tol=TOL, bins=None):
     """sklearn's _solve_svd (discriminant_analysis.py) restated on (G, class sums, counts): the SVD of the scaled,
-    within-class-centred data matrix is replaced by the eigen-decomposition of its 150 x 150 Gram matrix."""
+    within-class-centred data matrix is replaced by the eigen-decomposition of its 150 x 150 Gram matrix.
+    bins: the mel bins to fit (default all); the list returned follows their order."""
     N, xbar, G = stats['n'], stats['xbar'], stats['G']
     estimators = []
-    for b in range(stats['sums'].shape[0]):
+    for b in (range(stats['sums'].shape[0]) if bins is None else bins):
         present = np.nonzero(stats['counts'][b] > 0)[0]
         n_k = stats['counts'][b][present]
         K = len(present)

@@ -67,43 +67,29 @@ def compute_features(eeg, sfreq_eeg, audio, audio_sr):
 
 
 def train(eeg, audio, sfreq_eeg, sfreq_audio, bad_channels, nb_mel_bins=40):
-    """Host arrays in, host arrays + fitted estimators out, as in the reference - but the recording and the audio are moved to
-    the device once and every stage in between (channel selection, features, decimation, log-mel target, quantisation,
-    Spearman ranking, column selection, LDA statistics) works on device-resident tensors."""
-    import torch
+    """Host arrays in, host arrays + fitted estimators out, as in the reference (train.py:132-168) - every stage in between
+    (features, decimation, log-mel target, quantisation, Spearman ranking, column selection, LDA statistics) works on
+    device-resident tensors.  With torch.distributed initialised (one process per GPU, every rank passing the same arrays)
+    the job is sharded as sgs/training.py:sharded_fit describes - features + Spearman by channel block, LDA statistics by
+    row with one all-reduce - and every rank returns the same model."""
     from sgs import _lib
     _lib.ensure_init()
-    dev = torch.device('cuda', torch.cuda.current_device())
     eeg = np.asarray(eeg)
     if eeg.dtype not in (np.float32, np.float64):
         eeg = eeg.astype(np.float64)
-    eeg_d = torch.from_numpy(eeg).to(dev)
-    audio_d = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float64)).to(dev)
     if len(bad_channels) > 0:
         logger.info('EEG original shape: {} x {}'.format(*eeg.shape))
         mask = np.ones(eeg.shape[1], bool)
         mask[bad_channels] = False
-        eeg_d = eeg_d[:, torch.from_numpy(mask).to(dev)].contiguous()
-        logger.info('EEG truncated shape: {} x {}'.format(*eeg_d.shape))
+        eeg = eeg[:, mask]
+        logger.info('EEG truncated shape: {} x {}'.format(*eeg.shape))
     else:
         logger.info('No bad channels specified.')
-
-    x_train, y_train = compute_features(eeg_d, sfreq_eeg, audio_d, sfreq_audio)
-    del eeg_d, audio_d
-    y_train = y_train[20:-4]          # align the audio frames with the 20-frame context / 50 ms window of the features
-
-    medians, borders, q_spectrogram = quantization(y_train, nb_intervals=9)
-    select = feature_selection(x_train, y_train)
-    x_train = x_train[:, torch.from_numpy(np.ascontiguousarray(select, dtype=np.int64)).to(dev)].contiguous()
-
-    estimators = [None for _ in range(nb_mel_bins)]
-    y_train = q_spectrogram
+    x_train, y_train, medians, estimators, select = training.sharded_fit(eeg, audio, sfreq_eeg, sfreq_audio, nb_mel_bins)
     logger.info('x_train: ' + str(tuple(x_train.shape)))
     logger.info('y_train: ' + str(tuple(y_train.shape)))
-    minimum = min(len(x_train), len(y_train))
-    x_train = x_train[0:minimum, :]
-    y_train = y_train[0:minimum, :]
-    train_estimators(estimators=estimators, x_train=x_train, y_train=y_train)
+    for stage in ('features_s', 'target_quantization_s', 'spearman_s', 'lda_stats_s', 'eigen_solves_s'):
+        logger.info('Finished stage [{}] in {:.4f} seconds.'.format(stage[:-2], training.last_profile.get(stage, 0.0)))
     return x_train.cpu().numpy(), y_train.cpu().numpy(), medians, estimators, select
 
 
