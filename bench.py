@@ -136,6 +136,124 @@ def check_decompositions(decoder, x, _lib):
     return out
 
 
+
+# ---- BASELINE config 4: batched offline Griffin-Lim, 4096 utterances x 2 s, 32 iterations, sharded over the ranks ---------
+C4_UTT, C4_FRAMES, C4_ITERS = 4096, 200, 32
+
+
+def config4_leg(world, rank, dist, barrier):
+    """local.offline.griffin_lim semantics (offline.py:131-192: 800-point frames, complex phase projection) for 4096
+    utterances x 200 frames x 32 iterations, utterances sharded over the ranks with decode.session_shard (strong scaling,
+    no collective), inputs resident in HBM.  Device time of the job = max over ranks of CUDA-event time."""
+    import numpy as np
+    import torch
+    import decode as dec_mod
+    from sgs.griffinlim import griffin_lim_batch
+    from sgs.synth import default_medians
+    lo, hi = dec_mod.session_shard(C4_UTT, rank, world)
+    U, T = hi - lo, C4_FRAMES
+    med = torch.from_numpy(default_medians(40, 9)).cuda()
+    g = torch.Generator(device='cuda'); g.manual_seed(3000 + rank)
+    idx = torch.randint(0, 9, (U, T, 40), device='cuda', generator=g)
+    spec = torch.gather(med[None, None].expand(U, T, 40, 9), 3, idx[..., None])[..., 0].contiguous()   # per-bin logistic medians (SURVEY.md 8d)
+    noise = torch.rand((U, 160 * (T - 1) + 800), dtype=torch.float64, device='cuda', generator=g)
+    del idx
+    pcm = griffin_lim_batch(spec, noise, num_iterations=C4_ITERS)
+    reps = 2
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        pcm = griffin_lim_batch(spec, noise, num_iterations=C4_ITERS)
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b) / reps
+    if world > 1:
+        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # nominal flops: one forward + one inverse real 800-point transform per frame-iteration, 2.5 N log2 N each (SURVEY.md 8d)
+    flop = C4_UTT * T * C4_ITERS * 2 * 2.5 * 800 * np.log2(800)
+    out = {"workload": "config4: %d utterances x %d frames (2 s) x %d Griffin-Lim iterations, 800-point frames (local.offline.griffin_lim)" % (C4_UTT, T, C4_ITERS),
+           "utterances_per_rank": U, "ms": ms, "frame_iterations_per_s": C4_UTT * T * C4_ITERS / (ms * 1e-3),
+           "audio_seconds_per_s": C4_UTT * T * 0.01 / (ms * 1e-3), "scaling": "strong",
+           "fp64": {"achieved_flop_s_per_gpu": flop / world / (ms * 1e-3), "peak": 2 * FP64_PEAK, "frac": flop / world / (ms * 1e-3) / (2 * FP64_PEAK),
+                    "unit": "nominal fp64 flop/s per GPU (2.5 N log2 N per real transform) against 2 x the measured DFMA/s"},
+           "timing": "CUDA events around %d repetitions after 1 warm-up, max over ranks" % reps}
+    if rank == 0 and world == 1:
+        # CPU port on one utterance of the same batch: baseline and checker at once
+        O = _oracle()
+        t0 = time.perf_counter()
+        want = O.griffin_lim_offline(spec[0].cpu().numpy(), noise[0].cpu().numpy(), num_iterations=C4_ITERS)
+        dt = time.perf_counter() - t0
+        d = np.abs(pcm[0].cpu().numpy().astype(int) - want.astype(int))
+        assert d.max() <= 1, int(d.max())
+        out["cpu_baseline"] = {"frame_iterations_per_s": T * C4_ITERS / dt, "cores": 1, "kind": "port",
+                               "sample": "oracle.griffin_lim_offline, 1 utterance x %d frames x %d iterations" % (T, C4_ITERS),
+                               "gpu_vs_this_oracle_int16_max_diff_lsb": int(d.max())}
+    del spec, noise, pcm
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---- BASELINE config 3: train.train on a 128 ch x 1 h session ---------------------------------------------------------------------
+C3_SECONDS = float(os.environ.get('SGS_BENCH_C3_SECONDS', '3600'))
+
+
+def config3_leg(world, rank, dist, barrier):
+    """train.train (train.py:132-168) on 128 ch x 3600 s @ 2048 Hz + 48 kHz audio through the public entry point with HOST
+    arrays, as a `world`-rank job (sgs/training.py:sharded_fit: channel-block features + Spearman, row-sharded LDA
+    statistics, one all-reduce).  Wall time from the call to the returned model, max over ranks."""
+    import numpy as np
+    import torch
+    import train as train_mod
+    from sgs import synth, training
+    # every rank holds the same recording (made on the device for speed, then handed over as the host arrays the API takes)
+    eeg = synth.seeg_sessions_device([900], N_CH, SR, C3_SECONDS)[0].cpu().numpy()
+    audio = synth.audio_session_device(900, C3_SECONDS, 48000).cpu().numpy()
+    torch.cuda.empty_cache()
+    warm = int(20 * SR)
+    train_mod.train(eeg[:warm], audio[:20 * 48000], SR, 48000, [])            # plans, pools, NCCL communicator
+    barrier()
+    t0 = time.perf_counter()
+    x_train, q, medians, estimators, select = train_mod.train(eeg, audio, SR, 48000, [])
+    wall = time.perf_counter() - t0
+    prof = dict(training.last_profile)
+    if world > 1:
+        t = torch.tensor([wall], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        # every rank must hold the same model
+        h = torch.tensor([float(np.sum(select * np.arange(1, len(select) + 1))), float(sum(np.abs(e.coef_).sum() for e in estimators))],
+                         device='cuda', dtype=torch.float64)
+        lo, hi = h.clone(), h.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert lo[0].item() == hi[0].item() and abs(hi[1].item() - lo[1].item()) <= 1e-9 * abs(hi[1].item()), (lo, hi)
+    out = {"workload": "config3: train.train on %d ch x %g s @ %d Hz sEEG + 48 kHz audio, 5-tap context (model_order 4), 150 features, 40 bins x 9 classes"
+                       % (N_CH, C3_SECONDS, SR),
+           "wall_s": wall, "rows": int(x_train.shape[0]), "channel_seconds_per_s": N_CH * C3_SECONDS / wall,
+           "stage_s_rank0": {k: round(v, 4) for k, v in prof.items() if k.endswith('_s')},
+           "h2d_bytes_rank0": prof.get('h2d_bytes'),
+           "collectives_rank0": {"rho_allgather_bytes": prof.get('rho_allgather_bytes'), "columns_allreduce_bytes": prof.get('columns_allreduce_bytes'),
+                                 "columns_allreduce_us": round(1e6 * prof.get('columns_allreduce_s', 0.0), 1),
+                                 "stats_allreduce_bytes": prof.get('stats_allreduce_bytes'),
+                                 "stats_allreduce_us": round(1e6 * prof.get('stats_allreduce_s', 0.0), 1)},
+           "scaling": "strong", "timing": "host wall clock of one train.train call after a 20 s warm-up call, max over ranks"}
+    stages = out["stage_s_rank0"]
+    out["limiter"] = max((k for k in stages if k != 'total_s'), key=lambda k: stages[k])
+    if rank == 0 and world == 1:
+        O = _oracle()
+        sub = 30.0
+        n = int(sub * SR)
+        dec16 = np.ascontiguousarray(audio[:int(sub * 48000):3])          # the port takes 16 kHz audio (decimation is audio-side prep)
+        t0 = time.perf_counter()
+        O.train(eeg[:n].astype(np.float64), dec16, SR, [])
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"seconds": dt, "cores": 1, "kind": "port", "sample": "oracle.train (numpy/scipy/sklearn restatement of train.py:132-168) on the first %g s" % sub,
+                               "scaled_to_workload_s": dt * C3_SECONDS / sub, "channel_seconds_per_s": N_CH * sub / dt}
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -265,6 +383,12 @@ def run_ours(args):
     h2d = int(xh_np.nbytes)
     d2h = int(spec_h.nbytes + audio_h.nbytes)
 
+    del xh, xh_np, spec_h, audio_h
+    decoder._out_key = decoder._out_bufs = None
+    torch.cuda.empty_cache()
+    c4 = config4_leg(world, rank, dist, barrier) if not args.no_configs else None
+    c3 = config3_leg(world, rank, dist, barrier) if not args.no_configs else None
+
     if rank == 0:
         peaks = {}
         try:
@@ -330,6 +454,7 @@ def run_ours(args):
         }
         line["cpu_baseline"] = cpu_baseline_sample(decoder) if world == 1 else None      # rank 0 at N = 1 only (the other ranks would wait for it)
         line["latency"] = latency_leg() if world == 1 and not args.no_latency else None
+        line["config4"], line["config3"] = c4, c3
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -525,6 +650,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-latency', dest='no_latency', action='store_true')
+    ap.add_argument('--no-configs', dest='no_configs', action='store_true', help='skip the config3 / config4 sub-records')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

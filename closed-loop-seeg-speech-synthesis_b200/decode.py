@@ -12,8 +12,7 @@
     load_params / load_seeg / store_decoding_to_file
                                 the artefacts either side of a decoding run (decode.py:186-219, 299-313): params.h5, the
                                 sEEG recording, audio.wav, spectrogram.npy, sEEG.hdf.  HDF5 goes through h5py when it is
-                                importable; without it the same datasets are read from / written to .npz files of the
-                                same stem (what train.store_training_to_file writes in that case).
+                                importable and through the built-in flat-file reader / writer sgs/hdf5lite.py when not.
 """
 import os
 import logging
@@ -205,17 +204,33 @@ def setup_decoder(eeg_sender, sfreq, estimators_serialized, medians_array, bad_c
 
 
 def _read_datasets(path, names):
-    """Datasets `names` of an HDF5 file, or of the .npz of the same stem when h5py is absent or the .npz is what exists."""
+    """Datasets `names` of an HDF5 file: through h5py when it is importable, else through the built-in reader of the flat
+    layout these files have (sgs/hdf5lite.py); the .npz of the same stem is read when that is what exists (artefacts written
+    by round-1 builds of this package)."""
     stem = os.path.splitext(path)[0]
     if os.path.exists(path):
         try:
             import h5py
         except ImportError:
-            raise ImportError('{} is an HDF5 file and h5py is not importable; store the datasets as {}.npz'.format(path, stem))
+            from sgs import hdf5lite
+            return hdf5lite.read(path, names)
         with h5py.File(path, 'r') as hf:
             return {k: hf[k][...] for k in names}
     with np.load(stem + '.npz') as z:
         return {k: z[k] for k in names}
+
+
+def _write_datasets(path, datasets):
+    """HDF5 file with `datasets` in its root group (h5py when importable, else sgs/hdf5lite.py)."""
+    try:
+        import h5py
+    except ImportError:
+        from sgs import hdf5lite
+        hdf5lite.write(path, datasets)
+        return
+    with h5py.File(path, 'w') as hf:
+        for k, v in datasets.items():
+            hf.create_dataset(k, data=v)
 
 
 def load_params(session_dir):
@@ -230,20 +245,25 @@ def load_seeg(seeg_file):
     return d['sEEG'], int(np.asarray(d['sEEG_sr']).reshape((1,))[0])
 
 
-def store_decoding_to_file(run_dir, spectrogram, output_audio, received_sEEG, sfreq, config=None):
-    """audio.wav (16 kHz int16), sEEG.hdf, spectrogram.npy and decode.ini in run_dir (decode.py:186-219; the plot is
-    out of scope).  run_dir is an argument here - the reference reads a module global set by its __main__."""
+# set by the caller before store_decoding_to_file, as the reference's __main__ does (decode.py:259-267, 275)
+run_dir = None
+config = None
+
+
+def store_decoding_to_file(spectrogram, output_audio, received_sEEG, sfreq, run_dir=None, config=None):
+    """audio.wav (16 kHz int16), sEEG.hdf, spectrogram.npy and decode.ini (decode.py:186-219; the plot is out of scope).
+    The reference's signature; like there the target directory and the configuration default to the module globals
+    `run_dir` / `config`, and may be passed as keywords instead."""
     from scipy.io.wavfile import write as wavwrite
-    wavwrite(os.path.join(run_dir, 'audio.wav'), 16000, np.asarray(output_audio))
-    try:
-        import h5py
-        with h5py.File(os.path.join(run_dir, 'sEEG.hdf'), 'w') as hf:
-            hf.create_dataset('sEEG', data=received_sEEG)
-            hf.create_dataset('sEEG_sr', data=sfreq, dtype=np.int32)
-    except ImportError:
-        np.savez(os.path.join(run_dir, 'sEEG.npz'), sEEG=received_sEEG, sEEG_sr=np.int32(sfreq))
-    np.save(os.path.join(run_dir, 'spectrogram.npy'), spectrogram)
-    if config is not None:
-        with open(os.path.join(run_dir, 'decode.ini'), 'w') as configfile:
-            config.write(configfile)
-    logger.info('Decoding artefacts written to {}'.format(run_dir))
+    target = run_dir if run_dir is not None else globals()['run_dir']
+    cfg = config if config is not None else globals()['config']
+    if target is None:
+        raise ValueError('decode.run_dir is not set: assign it (as decode.py\'s __main__ does) or pass run_dir=...')
+    wavwrite(os.path.join(target, 'audio.wav'), 16000, np.asarray(output_audio))
+    logger.info('Decoded audio written to {}'.format(os.path.join(target, 'audio.wav')))
+    _write_datasets(os.path.join(target, 'sEEG.hdf'), {'sEEG': np.asarray(received_sEEG), 'sEEG_sr': np.int32(sfreq)})
+    np.save(os.path.join(target, 'spectrogram.npy'), spectrogram)
+    if cfg is not None:
+        with open(os.path.join(target, 'decode.ini'), 'w') as configfile:
+            cfg.write(configfile)
+    logger.info('Decoding artefacts written to {}'.format(target))

@@ -119,15 +119,16 @@ class FeaturePlan:
     def offline_window_starts(self, n_samples):
         """offline.py:105-106; returns (starts int32[W], length) in real-sample coordinates."""
         nw = self.offline_num_windows(n_samples)
-        starts = np.empty(nw, dtype=np.int64)
-        length = None
-        for k in range(nw):
-            s = int(round((k * self.window_shift) * self.sr))
-            e = int(round(s + self.window_length * self.sr))
-            starts[k] = s
-            assert length is None or e - s == length
-            length = e - s
-        if length is None:
+        # int(round(k * shift * sr)) for every k at once: np.rint rounds half to even like Python's round(), and the float64
+        # products are the ones the reference's loop forms (an hour of recording has 360 000 windows - as a Python loop this
+        # table cost more than the feature kernels)
+        k = np.arange(nw, dtype=np.float64)
+        starts = np.rint((k * self.window_shift) * self.sr).astype(np.int64)
+        ends = np.rint(starts + self.window_length * self.sr).astype(np.int64)
+        if nw:
+            length = int(ends[0] - starts[0])
+            assert int((ends - starts).min()) == length == int((ends - starts).max())
+        else:
             length = int(round(self.window_length * self.sr))
         return starts, length
 
@@ -139,14 +140,15 @@ class FeaturePlan:
         first_ms = (float(frame_size) / sr) * 1000.0
         shift_ms = self.frame_shift_ms
         total = self.zero_fill + n_samples
-        ends = []
-        k = 0
-        e = frame_size
-        while e <= total:
-            ends.append(e)
-            k += 1
-            e = round(((first_ms + k * shift_ms) / 1000.0) * sr)
-        return np.asarray(ends, dtype=np.int64)
+        # E_k = round(((first_ms + k * shift_ms) / 1000) * sr), k = 0, 1, ... while E_k <= total - vectorised (np.rint = Python's
+        # banker's round; the same float64 expression per k), with the count found from an over-estimate
+        n_guess = int(max(0.0, (total - frame_size) / (float(shift_ms) / 1000.0 * sr))) + 3
+        k = np.arange(n_guess, dtype=np.float64)
+        ends = np.rint(((first_ms + k * shift_ms) / 1000.0) * sr).astype(np.int64)
+        ends[0] = frame_size
+        stop = int(np.argmax(ends > total)) if (ends > total).any() else len(ends)
+        assert stop < n_guess
+        return ends[:stop]
 
     def online_window_starts(self, n_samples):
         """Online frames as (starts, length) in real-sample coordinates (negative = zero-fill region)."""

@@ -94,6 +94,7 @@ class FeatureExtractor:
     def scan_plan(self, n_samples, n_streams, chunks=None, horizon=None):
         """(n_chunks, chunk_len, horizon, phi-or-None)."""
         chunks = chunks if chunks is not None else os.environ.get('SGS_FEAT_CHUNKS')
+        explicit = chunks
         if chunks is None:
             groups = -(-n_streams // STREAMS_PER_BLOCK)
             want = max(1, int(round(SM_COUNT * BLOCKS_PER_SM / groups)))
@@ -108,6 +109,15 @@ class FeatureExtractor:
             return 1, int(n_samples), 0, None
         w = int(horizon) if horizon is not None else self.horizon()
         if w >= chunk_len:
+            if explicit is None:
+                # few streams, long recording (a channel block of a 1 h session): chunks of at least one horizon keep the
+                # truncated zero-state pass (work <= 2 T, no carry) where the short chunks above would need the exact carry -
+                # a serial walk over hundreds of chunks with one thread per stream (0.5 s for 64 streams x 7.4 M samples)
+                groups = -(-n_streams // STREAMS_PER_BLOCK)
+                long_len = max(-(-w // 64) * 64 + 64, -(-(-(-n_samples * groups // (2 * SM_COUNT))) // 64) * 64)
+                long_chunks = -(-n_samples // long_len)
+                if long_chunks >= 2 and groups * long_chunks >= SM_COUNT:
+                    return long_chunks, long_len, w, None
             return chunks, chunk_len, chunk_len, (self.phi(chunk_len) if chunks > 2 else None)
         return chunks, chunk_len, w, None
 

@@ -94,6 +94,35 @@ def audio_session(session, duration_s, sr=16000):
     return a + rng.normal(0, 0.0001, n)
 
 
+def audio_session_device(session, duration_s, sr=16000, device='cuda'):
+    """audio_session generated on the device (float64 torch tensor): the same envelope knots, pitch contour and harmonic
+    stack; the two noise terms come from torch's generator.  An hour at 48 kHz is 173 M samples - too slow to make on the
+    host inside a benchmark."""
+    import torch
+    kt, kv = _envelope(np.random.default_rng(5000 + session), duration_s)
+    n = int(round(duration_s * sr))
+    t = torch.arange(n, device=device, dtype=torch.float64) / float(sr)
+    knot_hz = 1.0 / (kt[1] - kt[0])
+    pos = t * knot_hz
+    i0 = pos.floor().long().clamp_(0, len(kv) - 2)
+    kvd = torch.from_numpy(kv).to(device)
+    frac = pos - i0.to(torch.float64)
+    g = kvd[i0] * (1.0 - frac) + kvd[i0 + 1] * frac
+    del pos, i0, frac
+    f0 = 120.0 + 30.0 * torch.sin(2 * np.pi * 0.7 * t)
+    ph = 2 * np.pi * torch.cumsum(f0, 0) / sr
+    del f0, t
+    a = torch.zeros(n, device=device, dtype=torch.float64)
+    for h, amp in enumerate([1.0, 0.6, 0.45, 0.3, 0.2, 0.15, 0.1, 0.08], start=1):
+        a += amp * torch.sin(h * ph + 0.3 * h)
+    del ph
+    gen = torch.Generator(device=device)
+    gen.manual_seed(2000 + session)
+    a = 0.15 * g * a + 0.004 * torch.randn(n, device=device, dtype=torch.float64, generator=gen)
+    a.clamp_(-0.5, 0.5)
+    return a + 0.0001 * torch.randn(n, device=device, dtype=torch.float64, generator=gen)
+
+
 def logmel_utterances(n_utt, n_frames, medians, seed=3000):
     """Config-4 style input: log-mels drawn from each bin's quantisation medians (n_utt x T x bins)."""
     rng = np.random.default_rng(seed)

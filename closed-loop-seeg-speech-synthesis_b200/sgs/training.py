@@ -203,9 +203,8 @@ class DeviceOps:
     """The device operators train.train is made of (libsgs through local/offline.py, sgs/spectrogram.py and this module)."""
 
     def upload(self, a, dtype=None):
-        import torch
-        a = np.ascontiguousarray(a) if dtype is None else np.ascontiguousarray(a, dtype=dtype)
-        return torch.from_numpy(a).to(torch.device('cuda', torch.cuda.current_device()))
+        from . import hostio
+        return hostio.upload(a, dtype)          # chunked through page-locked slots on several threads; gathers a strided channel block
 
     def sync(self):
         import torch
@@ -240,7 +239,8 @@ class DeviceOps:
         return a.contiguous()
 
     def to_host(self, a):
-        return a.cpu().numpy()
+        from . import hostio
+        return hostio.download(a)
 
     def col_means(self, x, select):
         return col_means(x, select)

@@ -90,27 +90,20 @@ def train(eeg, audio, sfreq_eeg, sfreq_audio, bad_channels, nb_mel_bins=40):
     logger.info('y_train: ' + str(tuple(y_train.shape)))
     for stage in ('features_s', 'target_quantization_s', 'spearman_s', 'lda_stats_s', 'eigen_solves_s'):
         logger.info('Finished stage [{}] in {:.4f} seconds.'.format(stage[:-2], training.last_profile.get(stage, 0.0)))
-    return x_train.cpu().numpy(), y_train.cpu().numpy(), medians, estimators, select
+    from sgs import hostio
+    return hostio.download(x_train), hostio.download(y_train), medians, estimators, select
 
 
 def store_training_to_file(config, x_train, y_train, medians, estimators, bad_channels, select):
-    """Writes LDAs.pkl, training_features.npy and params (train.py:171-205).  The reference stores params.h5 with
-    h5py; when h5py is not importable the same four datasets go to params.npz."""
+    """Writes LDAs.pkl, training_features.npy, params.h5 and train.ini (train.py:171-205; the plot is out of scope).
+    params.h5 is written with h5py when it is importable, else by sgs/hdf5lite.py - the same four root-group datasets."""
     base = os.path.join(config['General']['storage_dir'], config['General']['session'])
     with open(os.path.join(base, 'LDAs.pkl'), 'wb') as fh:
         pickle.dump(estimators, fh)
     np.save(os.path.join(base, 'training_features.npy'), x_train)
-    blob = np.void(pickle.dumps(estimators))
-    try:
-        import h5py
-        with h5py.File(os.path.join(base, 'params.h5'), 'w') as hf:
-            hf.create_dataset('bad_channels', data=bad_channels)
-            hf.create_dataset('medians_array', data=medians)
-            hf.create_dataset('estimators', data=blob)
-            hf.create_dataset('select', data=select)
-    except ImportError:
-        np.savez(os.path.join(base, 'params.npz'), bad_channels=np.asarray(bad_channels), medians_array=medians,
-                 estimators=np.frombuffer(blob.tobytes(), dtype=np.uint8), select=select)
+    from decode import _write_datasets
+    _write_datasets(os.path.join(base, 'params.h5'), {'bad_channels': np.asarray(bad_channels), 'medians_array': medians,
+                                                      'estimators': np.void(pickle.dumps(estimators)), 'select': select})
     with open(os.path.join(base, 'train.ini'), 'w') as configfile:
         config.write(configfile)
     logger.info('Training completed.')

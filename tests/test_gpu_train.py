@@ -165,3 +165,19 @@ def test_cross_validation_driver_above_chance():
     _, _, _, (mean_rand, _, _) = crossval.cross_validate(eeg, audio, sr, 16000, [2], norm_factor=10, nb_folds=3, randomize=True,
                                                          rng=np.random.default_rng(3))
     assert mean > 0.1 and mean > mean_rand + 0.1, (mean, mean_rand)       # measured: 0.21 against -0.02
+
+
+def test_hostio_pipelined_transfers_round_trip():
+    """sgs.hostio: chunked, multi-threaded pinned staging of pageable arrays - contiguous, a strided channel block, a long
+    vector with a ragged tail, a cast, and the small-array fall-back all arrive bit-identical."""
+    import torch
+    from sgs import hostio
+    rng = np.random.default_rng(3)
+    big = rng.standard_normal((700000, 48)).astype(np.float32)               # 134 MB
+    for a in (big, big[:, 5:21], big[::2, 7:8], rng.standard_normal(40_000_123), rng.standard_normal((50, 3))):
+        t = hostio.upload(a)
+        assert t.is_cuda and tuple(t.shape) == a.shape
+        assert np.array_equal(t.cpu().numpy(), a)
+        assert np.array_equal(hostio.download(t), a)
+    t = hostio.upload(big[:, :8], np.float64)
+    assert t.dtype == torch.float64 and np.array_equal(t.cpu().numpy(), big[:, :8].astype(np.float64))

@@ -213,7 +213,14 @@ def test_artefacts_round_trip(tmp_path):
 
     spec, audio = rng.normal(size=(30, 40)), rng.integers(-32768, 32767, 4800).astype(np.int16)
     seeg = rng.normal(size=(614, 8)).astype(np.float32)
-    decode.store_decoding_to_file(str(tmp_path), spec, audio, seeg, 2048, config=cfg)
+    with pytest.raises(ValueError):
+        decode.store_decoding_to_file(spec, audio, seeg, 2048)                # reference signature; needs decode.run_dir
+    decode.run_dir, decode.config = str(tmp_path), cfg                       # ... which the reference's __main__ sets as globals
+    try:
+        decode.store_decoding_to_file(spec, audio, seeg, 2048)
+    finally:
+        decode.run_dir = decode.config = None
+    assert (tmp_path / 'params.h5').exists() is False and (tmp_path / 's1' / 'params.h5').exists() and (tmp_path / 'sEEG.hdf').exists()
     sr, a2 = wavread(str(tmp_path / 'audio.wav'))
     assert sr == 16000 and a2.dtype == np.int16 and np.array_equal(a2, audio)
     assert np.array_equal(np.load(tmp_path / 'spectrogram.npy'), spec)
@@ -348,3 +355,89 @@ def test_feature_node_schedule_never_defers_a_frame(sr, shift_ms):
         total += n
         left -= n
     assert k > 5000 * 1000.0 / sr / shift_ms - 10
+
+
+def _params_like(rng):
+    import pickle
+    return {'bad_channels': np.array([3, 17]), 'medians_array': rng.normal(size=(40, 9)),
+            'estimators': np.void(pickle.dumps([{'coef_': rng.normal(size=(9, 150))} for _ in range(3)])),
+            'select': rng.permutation(640)[:150], 'sEEG': rng.normal(size=(614, 8)).astype(np.float32), 'sEEG_sr': np.int32(2048),
+            'no_bad_channels': np.array([]), 'u16': np.arange(7, dtype=np.uint16), 'i8_3d': rng.integers(-100, 100, (2, 3, 4)).astype(np.int8),
+            'scalar_f64': np.float64(3.25)}
+
+
+def test_hdf5lite_round_trip_and_file_structure(tmp_path):
+    """sgs/hdf5lite.py (the h5py-free reader / writer of params.h5 and sEEG.hdf): every dataset comes back with its dtype,
+    shape and bits, and the file has the structure the HDF5 specification prescribes for a version-0 superblock with a
+    symbol-table root group - signature, 96-byte superblock, end-of-file address, TREE / HEAP / SNOD blocks at the addresses
+    the superblock's root entry caches, entries in name order, 8-byte alignment of every object."""
+    import struct
+    from sgs import hdf5lite
+    rng = np.random.default_rng(5)
+    data = _params_like(rng)
+    path = str(tmp_path / 'params.h5')
+    hdf5lite.write(path, data)
+    back = hdf5lite.read(path)
+    assert sorted(back) == sorted(data)
+    for k, v in data.items():
+        got = back[k]
+        if isinstance(v, np.void):
+            assert isinstance(got, np.void) and got.tobytes() == v.tobytes()
+        else:
+            v = np.asarray(v)
+            assert np.asarray(got).dtype == v.dtype and np.asarray(got).shape == v.shape and np.array_equal(got, v), k
+    assert list(hdf5lite.read(path, ['select', 'sEEG_sr'])) == ['select', 'sEEG_sr']
+    with pytest.raises(KeyError):
+        hdf5lite.read(path, ['missing'])
+    raw = open(path, 'rb').read()
+    assert raw[:8] == b'\x89HDF\r\n\x1a\n' and raw[8:16] == bytes([0, 0, 0, 0, 0, 8, 8, 0])
+    leaf_k, internal_k, flags = struct.unpack_from('<HHI', raw, 16)
+    base, free, eof, driver = struct.unpack_from('<QQQQ', raw, 24)
+    assert (leaf_k, internal_k, flags, base) == (4, 16, 0, 0) and free == driver == 2 ** 64 - 1 and eof == len(raw)
+    name_off, root_hdr, cache, _, btree, heap = struct.unpack_from('<QQIIQQ', raw, 56)
+    assert (name_off, root_hdr, cache) == (0, 96, 1)
+    assert raw[btree:btree + 4] == b'TREE' and raw[heap:heap + 4] == b'HEAP'
+    # the root object header carries the same two addresses in its symbol-table message (type 0x0011)
+    version, n_msgs, refs, size = struct.unpack_from('<BxHII', raw, root_hdr)
+    mtype, msize = struct.unpack_from('<HH', raw, root_hdr + 16)
+    assert (version, n_msgs, refs, mtype, msize) == (1, 1, 1, 0x11, 16) and struct.unpack_from('<QQ', raw, root_hdr + 24) == (btree, heap)
+    ntype, level, used, left, right, key0 = struct.unpack_from('<BBHQQQ', raw, btree + 4)
+    assert (ntype, level, used, key0) == (0, 0, 2, 0) and left == right == 2 ** 64 - 1          # 10 datasets = two leaf nodes of <= 8
+    seg_size, free_head, seg = struct.unpack_from('<QQQ', raw, heap + 8)
+    assert free_head == 1 and seg % 8 == 0 and raw[seg:seg + 8] == bytes(8)
+    names = []
+    for i in range(used):
+        child, key = struct.unpack_from('<QQ', raw, btree + 32 + 16 * i)
+        assert raw[child:child + 4] == b'SNOD' and child % 8 == 0
+        n = struct.unpack_from('<H', raw, child + 6)[0]
+        for j in range(n):
+            off, hdr = struct.unpack_from('<QQ', raw, child + 8 + 40 * j)
+            assert hdr % 8 == 0 and raw[hdr] == 1
+            names.append(raw[seg + off:raw.index(b'\x00', seg + off)].decode())
+        assert raw[seg + key:raw.index(b'\x00', seg + key)].decode() == names[-1]             # key = largest name of the child to its left
+    assert names == sorted(data, key=lambda s: s.encode())
+    with pytest.raises(hdf5lite.Hdf5LiteError):
+        hdf5lite.write(str(tmp_path / 'bad.h5'), {'strings': np.array(['a', 'b'])})
+    (tmp_path / 'junk.h5').write_bytes(b'not an hdf5 file' * 100)
+    with pytest.raises(hdf5lite.Hdf5LiteError):
+        hdf5lite.read(str(tmp_path / 'junk.h5'))
+
+
+def test_hdf5lite_interchanges_with_h5py_when_present(tmp_path):
+    """Runs only where h5py is importable (not in the build image): files written by either side are read by the other."""
+    h5py = pytest.importorskip('h5py')
+    from sgs import hdf5lite
+    rng = np.random.default_rng(6)
+    data = _params_like(rng)
+    ours, theirs = str(tmp_path / 'ours.h5'), str(tmp_path / 'theirs.h5')
+    hdf5lite.write(ours, data)
+    with h5py.File(ours, 'r') as hf:
+        for k, v in data.items():
+            got = hf[k][()]
+            assert (got.tobytes() == v.tobytes()) if isinstance(v, np.void) else np.array_equal(got, v), k
+    with h5py.File(theirs, 'w') as hf:
+        for k, v in data.items():
+            hf.create_dataset(k, data=v)
+    back = hdf5lite.read(theirs)
+    for k, v in data.items():
+        assert (back[k].tobytes() == v.tobytes()) if isinstance(v, np.void) else np.array_equal(back[k], v), k
