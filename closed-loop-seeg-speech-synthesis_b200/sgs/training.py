@@ -152,6 +152,8 @@ def distributed_lda_stats(x_local, select, labels_local, n_classes=9, group=None
 # gloo (tests/test_train_host.py); DeviceOps below is the product binding.
 
 def _dist(group=None):
+    if group is False:
+        return None, 0, 1
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -199,10 +201,18 @@ def _allgather_objects(obj, group=None):
     return out
 
 
+def _torch_dtype(dtype):
+    import torch
+    return torch.from_numpy(np.empty(0, dtype=dtype)).dtype
+
+
 class DeviceOps:
     """The device operators train.train is made of (libsgs through local/offline.py, sgs/spectrogram.py and this module)."""
 
     def upload(self, a, dtype=None):
+        if _lib._is_torch(a):                   # already resident (the many-fold driver keeps the recording on the device)
+            import torch
+            return (a if dtype is None else a.to(_torch_dtype(dtype))).contiguous()
         from . import hostio
         return hostio.upload(a, dtype)          # chunked through page-locked slots on several threads; gathers a strided channel block
 
@@ -252,13 +262,17 @@ class DeviceOps:
 last_profile = {}       # stage times / collective sizes of the last sharded_fit in this process (bench.py's config3 record)
 
 
-def sharded_fit(eeg, audio, sfreq_eeg, sfreq_audio, nb_mel_bins=40, nb_intervals=9, nb_feats=150, ops=None, group=None):
+def sharded_fit(eeg, audio, sfreq_eeg, sfreq_audio, nb_mel_bins=40, nb_intervals=9, nb_feats=150, ops=None, group=None,
+                distributed=True):
     """train.py:132-168 after the bad-channel mask, on `world` ranks (see the block comment above; world = 1 is the
-    single-GPU path).  eeg (T x C) and audio are HOST arrays, the same on every rank.
+    single-GPU path).  eeg (T x C) and audio are HOST arrays, the same on every rank (device tensors are taken as they are).
+    distributed=False fits on this rank alone even when a process group exists (the many-fold driver shards whole folds).
     Returns (x_train[:, select] (device / ops array), labels, medians, estimators, select)."""
     import time
     ops = ops or DeviceOps()
-    dist, rank, world = _dist(group)
+    dist, rank, world = _dist(group) if distributed else (None, 0, 1)
+    if not distributed:
+        group = False                       # the collectives below become no-ops
     prof = {'world': world}
     t_all = time.perf_counter()
 
@@ -271,7 +285,7 @@ def sharded_fit(eeg, audio, sfreq_eeg, sfreq_audio, nb_mel_bins=40, nb_intervals
     t0 = time.perf_counter()
     eeg_d = ops.upload(eeg[:, c0:c1])
     audio_d = ops.upload(audio, np.float64)
-    prof['h2d_bytes'] = int(eeg[:, c0:c1].nbytes + np.asarray(audio).size * 8)
+    prof['h2d_bytes'] = 0 if _lib._is_torch(eeg) else int(eeg[:, c0:c1].nbytes + np.asarray(audio).size * 8)
     lap('h2d_s', t0)
 
     t0 = time.perf_counter()

@@ -165,6 +165,13 @@ def test_cross_validation_driver_above_chance():
     _, _, _, (mean_rand, _, _) = crossval.cross_validate(eeg, audio, sr, 16000, [2], norm_factor=10, nb_folds=3, randomize=True,
                                                          rng=np.random.default_rng(3))
     assert mean > 0.1 and mean > mean_rand + 0.1, (mean, mean_rand)       # measured: 0.21 against -0.02
+    assert crossval.last_profile['folds_on_this_rank'] == 3 and crossval.last_profile['total_s'] > 0
+    # the device-resident folds (recording uploaded once, model handed from train to decode in the process) give what the
+    # reference-signature worker gives from host arrays fold by fold (eval_steps/exp1.py:26-38)
+    host = [crossval.train_decode_worker(*a) for a in crossval.construct_folds(eeg, audio, sr, 16000, [2], 10, nb_folds=3)]
+    reco_h = np.vstack([r[:min(len(r), len(o))] for _, r, o, _ in host])
+    orig_h = np.vstack([np.asarray(o)[:min(len(r), len(o))] for _, r, o, _ in host])
+    assert np.array_equal(reco_h, reco) and np.array_equal(orig_h, orig)
 
 
 def test_hostio_pipelined_transfers_round_trip():

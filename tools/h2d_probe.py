@@ -6,8 +6,9 @@ For every rank: the GPU's PCI address and NUMA node, the CPUs / memory nodes thi
 (one cudaMemcpyAsync of 1 GiB per repetition, CUDA-event timed)
   alone        one GPU copying at a time, buffer placed by the default policy
   all_default  all N GPUs copying at once, buffers placed by the default (first-touch) policy
-  all_local    all at once, every buffer bound (set_mempolicy MPOL_BIND before the allocation) to its GPU's own NUMA node
-  all_node0    all at once, every buffer bound to node 0
+  all_node<k>  all at once, every buffer bound (set_mempolicy MPOL_BIND before the allocation) to NUMA node k, for every
+               online node: tells which node is local to which GPU even where sysfs reports numa_node = -1
+  all_best     all at once, every buffer on the node that gave its GPU the highest rate in the all_node<k> passes
 Rank 0 prints one JSON object.  The aggregate of `all_*` is the ceiling of the 8-GPU end-to-end number."""
 import ctypes
 import json
@@ -25,7 +26,7 @@ SYS_set_mempolicy = 238            # x86_64
 def set_mempolicy(node):
     """Bind this thread's future page allocations to one NUMA node (None = default policy).  Returns 0 on success."""
     libc = ctypes.CDLL(None, use_errno=True)
-    if node is None:
+    if node is None or node < 0:
         return libc.syscall(SYS_set_mempolicy, MPOL_DEFAULT, None, 0)
     mask = ctypes.c_ulong(1 << node)
     return libc.syscall(SYS_set_mempolicy, MPOL_BIND, ctypes.byref(mask), ctypes.c_ulong(64))
@@ -106,8 +107,16 @@ def main():
             alone = copy_rate(dst, buf)
         barrier()
     res['alone'] = gather(round(alone, 2))
-    for name, want in (('all_default', None), ('all_local', node), ('all_node0', 0)):
-        if name != 'all_default':
+    def online_nodes():
+        out = []
+        for part in (read('/sys/devices/system/node/online') or '0').split(','):
+            lo, _, hi = part.partition('-')
+            out += list(range(int(lo), int(hi or lo) + 1))
+        return out
+
+    def concurrent(name, want):
+        nonlocal buf
+        if want is not None:
             del buf
             buf, rc = pinned(GIB, want)
             info['set_mempolicy_rc_' + name] = rc
@@ -117,6 +126,13 @@ def main():
         barrier()
         per = gather(round(rate, 2))
         res[name] = {"per_gpu_gbs": per, "aggregate_gbs": round(sum(per), 1)}
+        return rate
+
+    concurrent('all_default', None)
+    by_node = {k: concurrent('all_node%d' % k, k) for k in online_nodes()}
+    best = max(by_node, key=by_node.get)
+    info['best_node'] = best
+    concurrent('all_best', best)
     infos = gather(info)
     if rank == 0:
         print(json.dumps({"gpus": world, "bytes_per_copy": GIB, "ranks": infos, "h2d_gbs": res}), flush=True)
