@@ -366,6 +366,24 @@ def run_ours(args):
     xh_np = xh.numpy()
     del x
     torch.cuda.empty_cache()
+    # the ceiling of this leg: raw pinned host-to-device copies of the same buffer, all ranks at once (one cudaMemcpyAsync of
+    # 2 GiB per repetition, CUDA events) - what the box's PCIe links and host memory deliver with nothing else going on
+    probe_bytes = min(2 << 30, xh.numel() * 4)
+    probe_src = xh.view(-1)[:probe_bytes // 4]
+    probe_dst = torch.empty(probe_bytes // 4, dtype=torch.float32, device='cuda')
+    probe_dst.copy_(probe_src, non_blocking=True)
+    barrier()
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    for _ in range(3):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    pb.record()
+    barrier()
+    h2d_rate = torch.tensor([3 * probe_bytes / (pa.elapsed_time(pb) * 1e-3) / 1e9], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(h2d_rate, op=dist.ReduceOp.SUM)
+    h2d_ceiling = float(h2d_rate.item())
+    del probe_dst, probe_src
     for _ in range(2):
         spec_h, audio_h = decoder.decode(xh_np, None, 11, pinned_outputs=True)
     barrier()
@@ -423,7 +441,9 @@ def run_ours(args):
                        "feature_scan": {"decomposition": "4 x SM-count equal pieces of the concatenated stream-group time lines (one CTA per SM, four pipelines of four stage warps each)", "horizon": hor},
                        "e2e_sessions_per_step": Se, "cpus_bound_to_gpu_numa_node": numa_cpus},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3, "api": "decode.OfflineDecoder.decode(numpy pinned, pinned_outputs=True) -> numpy; H2D / compute / D2H double-buffered per session"},
+                    "ms_per_step": e2e_s * 1e3, "h2d_ceiling_gbs": h2d_ceiling, "h2d_achieved_gbs": world * h2d / e2e_s / 1e9,
+                    "fraction_of_h2d_ceiling": world * h2d / e2e_s / 1e9 / h2d_ceiling,
+                    "h2d_ceiling_source": "measured in this run: all %d ranks copying 2 GiB of pinned host memory to their GPU at once (sum of the per-rank CUDA-event rates)" % world, "api": "decode.OfflineDecoder.decode(numpy pinned, pinned_outputs=True) -> numpy; H2D / compute / D2H double-buffered per session"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": ("k_iir_pieces<FEAT>" if pieces else "k_iir_stages<FEAT>") + " (feature extraction, pass 2; with pass 1 the largest stage of the step)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,

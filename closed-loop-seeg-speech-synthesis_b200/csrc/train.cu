@@ -225,37 +225,50 @@ int colminmax_run(const double* y, long long n, int ncol, double* mn, double* mx
 // Spearman rho of every column of x (n x ncol, row stride given) against the row mean of y (n x ny).
 int spearman_run(const double* x, long long n, int ncol, long long row_stride, const double* y, int ny, double* rho,
                  double* colsum, cudaStream_t st) {
-    SGS_ARG((long long)(ncol + 1) * n < 2147483647LL, "too many elements for the segmented sort (%lld)", (long long)(ncol + 1) * n);
+    // Columns are ranked in batches of ~64 M elements, each batch with the target as its last segment: the scratch (three
+    // double and two int arrays per element + the sort's own) stays below 3 GB whatever the recording - all 640 columns of a
+    // 1 h session at once took 10 GB, and growing the stream-ordered pool by that much on the first call cost 0.4 s, ten
+    // times the ranking itself.  A column's result does not depend on the batch it is ranked in.
+    SGS_ARG(n >= 1 && n < 1073741824LL, "bad row count %lld", n);
+    const long long per_batch_elems = 64LL << 20;
+    int batch = (int)(per_batch_elems / n);
+    batch = batch < 1 ? 1 : (batch > ncol ? ncol : batch);
+    SGS_ARG((long long)(batch + 1) * n < 2147483647LL, "too many elements for the segmented sort (%lld)", (long long)(batch + 1) * n);
     ProfScope ps(kProfTrain, st);
-    const int nseg = ncol + 1;                              // last segment = the target
+    const int nseg_max = batch + 1;                          // last segment of a batch = the target
     double *xt = nullptr, *keys = nullptr, *ranks = nullptr;
     int *idx_in = nullptr, *idx_out = nullptr, *offs = nullptr;
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
-    const size_t tot = (size_t)nseg * n;
-    SGS_CUDA(cudaMallocAsync((void**)&xt, sizeof(double) * tot, st));
-    SGS_CUDA(cudaMallocAsync((void**)&keys, sizeof(double) * tot, st));
-    SGS_CUDA(cudaMallocAsync((void**)&ranks, sizeof(double) * tot, st));
-    SGS_CUDA(cudaMallocAsync((void**)&idx_in, sizeof(int) * tot, st));
-    SGS_CUDA(cudaMallocAsync((void**)&idx_out, sizeof(int) * tot, st));
-    SGS_CUDA(cudaMallocAsync((void**)&offs, sizeof(int) * (nseg + 1), st));
-    k_transpose<<<dim3(ceil_div(n, 32), ceil_div(ncol, 32)), dim3(32, 8), 0, st>>>(x, n, ncol, row_stride, xt);
-    SGS_LAUNCHED();
-    k_rowmean<<<ceil_div(n, 256), 256, 0, st>>>(y, n, ny, xt + (size_t)ncol * n);
-    SGS_LAUNCHED();
-    k_iota<<<ceil_div((long long)tot, 256), 256, 0, st>>>(idx_in, n, nseg);
-    SGS_LAUNCHED();
-    std::vector<int> h_offs(nseg + 1);
-    for (int s = 0; s <= nseg; ++s) h_offs[s] = (int)((long long)s * n);
-    SGS_CUDA(cudaMemcpyAsync(offs, h_offs.data(), sizeof(int) * (nseg + 1), cudaMemcpyHostToDevice, st));
-    SGS_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, xt, keys, idx_in, idx_out, (int)tot, nseg, offs, offs + 1, 0, 64, st));
+    const size_t tot_max = (size_t)nseg_max * n;
+    SGS_CUDA(cudaMallocAsync((void**)&xt, sizeof(double) * tot_max, st));
+    SGS_CUDA(cudaMallocAsync((void**)&keys, sizeof(double) * tot_max, st));
+    SGS_CUDA(cudaMallocAsync((void**)&ranks, sizeof(double) * tot_max, st));
+    SGS_CUDA(cudaMallocAsync((void**)&idx_in, sizeof(int) * tot_max, st));
+    SGS_CUDA(cudaMallocAsync((void**)&idx_out, sizeof(int) * tot_max, st));
+    SGS_CUDA(cudaMallocAsync((void**)&offs, sizeof(int) * (nseg_max + 1), st));
+    std::vector<int> h_offs(nseg_max + 1);
+    for (int s = 0; s <= nseg_max; ++s) h_offs[s] = (int)((long long)s * n);
+    SGS_CUDA(cudaMemcpyAsync(offs, h_offs.data(), sizeof(int) * (nseg_max + 1), cudaMemcpyHostToDevice, st));
+    SGS_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, xt, keys, idx_in, idx_out, (int)tot_max, nseg_max, offs, offs + 1, 0, 64, st));
     SGS_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
-    SGS_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp, tmp_bytes, xt, keys, idx_in, idx_out, (int)tot, nseg, offs, offs + 1, 0, 64, st));
-    SGS_LAUNCHED();
-    k_avg_ranks<<<ceil_div((long long)tot, 256), 256, 0, st>>>(keys, idx_out, n, nseg, ranks);
-    SGS_LAUNCHED();
-    k_rank_corr<<<ncol, 256, 0, st>>>(ranks, ranks + (size_t)ncol * n, xt, n, rho, colsum);
-    SGS_LAUNCHED();
+    for (int c0 = 0; c0 < ncol; c0 += batch) {
+        const int nb = ncol - c0 < batch ? ncol - c0 : batch, nseg = nb + 1;
+        const size_t tot = (size_t)nseg * n;
+        k_transpose<<<dim3(ceil_div(n, 32), ceil_div(nb, 32)), dim3(32, 8), 0, st>>>(x + c0, n, nb, row_stride, xt);
+        SGS_LAUNCHED();
+        k_rowmean<<<ceil_div(n, 256), 256, 0, st>>>(y, n, ny, xt + (size_t)nb * n);
+        SGS_LAUNCHED();
+        k_iota<<<ceil_div((long long)tot, 256), 256, 0, st>>>(idx_in, n, nseg);
+        SGS_LAUNCHED();
+        size_t need = tmp_bytes;
+        SGS_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp, need, xt, keys, idx_in, idx_out, (int)tot, nseg, offs, offs + 1, 0, 64, st));
+        SGS_LAUNCHED();
+        k_avg_ranks<<<ceil_div((long long)tot, 256), 256, 0, st>>>(keys, idx_out, n, nseg, ranks);
+        SGS_LAUNCHED();
+        k_rank_corr<<<nb, 256, 0, st>>>(ranks, ranks + (size_t)nb * n, xt, n, rho + c0, colsum + c0);
+        SGS_LAUNCHED();
+    }
     cudaFreeAsync(xt, st); cudaFreeAsync(keys, st); cudaFreeAsync(ranks, st); cudaFreeAsync(idx_in, st);
     cudaFreeAsync(idx_out, st); cudaFreeAsync(offs, st); cudaFreeAsync(tmp, st);
     SGS_CUDA(cudaGetLastError());
