@@ -127,17 +127,19 @@ int sgs_gl_node_create(sgs_gl_node** node, int fft_size, int hop, int block_len,
     tf[0] = cplx{1, 0}; tf[kFft / 4] = cplx{0, -1}; tf[kFft / 2] = cplx{-1, 0};
     for (int k = 1; k < kFft / 4; ++k) tf[kFft / 2 - k] = cplx{-tf[k].x, tf[k].y};      // w[128 - k] = -conj(w[k]) to the bit (gl_blocks8.cuh relies on it)
     // W128^(l k1) for the register-FFT kernel (gl_blocks8.cuh): [k1][l] with rows padded to 9 entries
-    std::vector<cplx> tt(16 * 9, cplx{0, 0});
-    for (int k1 = 0; k1 < 16; ++k1)
-        for (int l = 0; l < 8; ++l) {
-            const int ex = (l * k1) % kHalf;
-            cplx w{cos(2.0 * pi * ex / kHalf), -sin(2.0 * pi * ex / kHalf)};
-            if (ex == 0) w = cplx{1, 0};
-            else if (ex == kHalf / 4) w = cplx{0, -1};
-            else if (ex == kHalf / 2) w = cplx{-1, 0};
-            else if (ex == 3 * kHalf / 4) w = cplx{0, 1};
-            tt[k1 * 9 + l] = w;
-        }
+    // second table: W128^((l + 48) k1) for the lanes of STFT frame 1, which hold point m in register slot (m + 10) mod 16
+    std::vector<cplx> tt(2 * 16 * 9, cplx{0, 0});
+    for (int f = 0; f < 2; ++f)
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int l = 0; l < 8; ++l) {
+                const int ex = ((l + 48 * f) * k1) % kHalf;
+                cplx w{cos(2.0 * pi * ex / kHalf), -sin(2.0 * pi * ex / kHalf)};
+                if (ex == 0) w = cplx{1, 0};
+                else if (ex == kHalf / 4) w = cplx{0, -1};
+                else if (ex == kHalf / 2) w = cplx{-1, 0};
+                else if (ex == 3 * kHalf / 4) w = cplx{0, 1};
+                tt[(f * 16 + k1) * 9 + l] = w;
+            }
     cudaError_t e = upload((void**)&n->d_window, window, sizeof(double) * kFft);
     if (e == cudaSuccess) e = upload((void**)&n->d_tw_t, tt.data(), sizeof(cplx) * tt.size());
     if (e == cudaSuccess) e = upload((void**)&n->d_ola, ola_window, sizeof(double) * kBlk);

@@ -15,7 +15,22 @@
 // expressed with register selects so that the expensive exp(angle) code runs without divergence.  The inverse runs
 // the mirrored pipeline (8-point FFT over k2, twiddle, transposition, 16-point FFT over k1) on conjugated data.
 // A warp works on two blocks at once: group g = lane / 8 handles block g / 2, STFT frame g % 2 (offsets 0 and 160).
-// The transposition buffer aliases the block's waveform buffer, which is dead between analysis and synthesis.
+//
+// The WAVEFORM STAYS IN REGISTERS across iterations.  The first register-FFT version wrote the synthesis result to shared
+// memory and read it back for the next analysis; it was co-limited by the shared-memory data pipe (64 % busy: 832 wavefronts
+// per warp-iteration - every LDS.128 / STS.128 of a warp is 4 wavefronts, broadcast across the four 8-lane groups does not
+// merge) and the FP64 pipe (54 %).  A lane's synthesis output r[l8 + 8m] is exactly the sample pair its next analysis reads,
+// except in the overlap of the two STFT frames (block samples 160..255): frame 0 holds them at m = 10..15, frame 1 at
+// m = 0..5, SAME l8.  Frame 1 therefore keeps point m in register slot (m + 10) mod 16 - a circular shift of the 16-point
+// transform's input, i.e. a phase W16^(6 k1) on its output, folded into frame 1's own twiddle table W128^((l + 48) k1) - so
+// that both frames hold the overlap in slots 10..15 and ONE xor-8 shuffle + add of 6 complex registers replaces the store /
+// load-add-store / load round trip; the synthesis and analysis windows (the same two doubles per register) are loaded once.
+//
+// The phase step runs in three passes over the lane's 8 partner pairs: (A) real-FFT split of both bins of every pair - the
+// partner's split reuses the products of the first (w[128-k] = -conj(w[k]) to the bit) - which leaves 16 (re, im) values in
+// the registers that held the spectrum; (B) exp(angle) of the 16 values, FOUR interleaved per call (exp_angle.cuh);
+// (C) Z = S exp(angle) and the inverse split.  Per-block set-up (40 exp() and the 2-tap inverse mel matrix) reads its tables
+// from shared memory without branches: it was 17 % of the kernel's stall samples, all of them waiting on dependent loads.
 #pragma once
 
 namespace sgs {
@@ -70,25 +85,11 @@ __device__ __forceinline__ void dft8(cplx (&v)[8]) {
 
 struct G8Tables {
     const double* window;      // blackman(256)
-    const cplx* tw_t;          // [16][9]: W128^(l k1) at [k1 * 9 + l]
+    const cplx* tw_t;          // [2][16][9]: W128^((l + 48 f) k1) at [(16 f + k1) * 9 + l]
     const cplx* tw_full;       // exp(-2 pi i k / 256), k <= 128
     const int* inv_idx;
     const double* inv_w;
 };
-
-// one real-FFT bin pair (kk, 128 - kk): split, Z = S exp(angle X), inverse split (stored conjugated); identical
-// arithmetic to the shared-memory kernel
-__device__ __forceinline__ void g8_pair(const double* s_ea, cplx& A, cplx& B, cplx w, cplx w2, double s1, double s2) {
-    const cplx d1 = cplx{A.x - B.x, A.y + B.y}, t1 = cmul(w, d1);
-    const double re1 = 0.5 * (A.x + B.x) + 0.5 * t1.y, im1 = 0.5 * (A.y - B.y) - 0.5 * t1.x;
-    const cplx d2 = cplx{B.x - A.x, B.y + A.y}, t2 = cmul(w2, d2);
-    const double re2 = 0.5 * (B.x + A.x) + 0.5 * t2.y, im2 = 0.5 * (B.y - A.y) - 0.5 * t2.x;
-    const double2 ea = exp_angle_pair_call(s_ea, im1, re1, im2, re2);
-    const double z1 = s1 * ea.x, z2 = s2 * ea.y;
-    const double sm = z1 + z2, df = z1 - z2;
-    A = cplx{fma(w.y, df, sm), -(w.x * df)};
-    B = cplx{fma(w2.y, -df, sm), w2.x * df};
-}
 
 // magnitudes are stored as partner pairs (S[p], S[128 - p]) at index p <= 64, so the phase step fetches both with one load
 // and carry the inverse transform's 1/256 (a power of two: scaling the magnitudes instead of the 256 output samples changes no bit)
@@ -99,6 +100,24 @@ __device__ __forceinline__ void g8_store_mag(double* S, int bin, double v) {
 }
 
 __device__ __forceinline__ cplx csel(bool c, cplx a, cplx b) { return {c ? a.x : b.x, c ? a.y : b.y}; }
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// synthesis x = irfft(Z0) w at 0 (+) irfft(Z1) w at 160 from v = conj(x~) of slot s at v[pos16(s)]; ANALYSE: multiplied by the
+// window again for the next iteration's transform (the window pair of a slot is loaded once for both)
+template <bool ANALYSE>
+__device__ __forceinline__ void g8_synthesis(cplx (&v)[16], const double2* win_lo, const double2* win_hi) {
+    cplx x[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const double2 wv = (s < 10 ? win_lo : win_hi)[8 * s];
+        cplx r = cplx{v[pos16(s)].x * wv.x, -v[pos16(s)].y * wv.y};
+        // block samples 160..255 sit in slots 10..15 of both frames' lanes with the same l8: x = r0 + r1
+        if (s >= 10) r = cplx{r.x + shfl_xor_f64(r.x, 8), r.y + shfl_xor_f64(r.y, 8)};
+        x[s] = ANALYSE ? cplx{r.x * wv.x, r.y * wv.y} : r;
+    }
+#pragma unroll
+    for (int s = 0; s < 16; ++s) v[s] = x[s];
+}
 
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
@@ -108,23 +127,34 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_window = reinterpret_cast<double*>(smem_raw);                 // [256]
     cplx* s_tw_full = reinterpret_cast<cplx*>(s_window + kFft);             // [130]
-    cplx* s_tw_t = s_tw_full + kG8SLen;                                     // [16 * 9]
-    double* s_ea = reinterpret_cast<double*>(s_tw_t + kG8BufCplx);          // [72] constants of exp(angle)
+    cplx* s_tw_t = s_tw_full + kG8SLen;                                     // [2][16 * 9]
+    double2* s_inv_w = reinterpret_cast<double2*>(s_tw_t + 2 * kG8BufCplx); // [130] the two inverse-mel taps of each bin
+    int2* s_inv_i = reinterpret_cast<int2*>(s_inv_w + kG8SLen);             // [130] their mel indices
+    double* s_ea = reinterpret_cast<double*>(s_inv_i + kG8SLen);            // [520] constants of exp(angle)
     G8WarpSmem* ws_all = reinterpret_cast<G8WarpSmem*>(s_ea + kEaTabLen);
     exp_angle_load_table(s_ea);
     for (int i = threadIdx.x; i < kFft; i += blockDim.x) s_window[i] = tab.window[i];
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) s_tw_full[i] = tab.tw_full[i];
-    for (int i = threadIdx.x; i < kG8BufCplx; i += blockDim.x) s_tw_t[i] = tab.tw_t[i];
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+        s_tw_full[i] = tab.tw_full[i];
+        s_inv_w[i] = make_double2(tab.inv_w[2 * i], tab.inv_w[2 * i + 1]);
+        s_inv_i[i] = make_int2(tab.inv_idx[2 * i], tab.inv_idx[2 * i + 1]);
+    }
+    for (int i = threadIdx.x; i < 2 * kG8BufCplx; i += blockDim.x) s_tw_t[i] = tab.tw_t[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l8 = lane & 7, grp = lane >> 3, blk = grp >> 1, frm = grp & 1;
-    const bool lane0 = l8 == 0;
+    const bool lane0 = l8 == 0, f1 = frm != 0;
     const int row_a = l8, row_b = lane0 ? 8 : 16 - l8;
     G8WarpSmem& ws = ws_all[warp];
-    double* x = ws.xb[blk];                                                 // this block's waveform
-    cplx* buf = reinterpret_cast<cplx*>(ws.xb[blk]) + frm * kG8BufCplx;     // this group's transposition buffer (aliases x)
-    const double* Sg = ws.S[blk][frm];
+    double* em = ws.xb[blk] + kBlk + frm * kG8MelMax;                       // set-up scratch behind the transposition buffers' first 480 doubles
+    cplx* buf = reinterpret_cast<cplx*>(ws.xb[blk]) + frm * kG8BufCplx;     // this group's transposition buffer
+    double* Sw = ws.S[blk][frm];
+    // register slot s holds point n = l8 + 8 ((s + c) & 15), c = 6 for frame 1: window pair / block sample pair of slot s
+    const double2* win_lo = reinterpret_cast<const double2*>(s_window) + l8 + (f1 ? 48 : 0);   // s < 10:  win_lo[8 s]
+    const double2* win_hi = reinterpret_cast<const double2*>(s_window) + l8 - (f1 ? 80 : 0);   // s >= 10: win_hi[8 s]
+    const int pos_lo = frm * kHop + 2 * l8 + (f1 ? 96 : 0), pos_hi = 2 * l8;                  // block sample = pos + 16 s
+    const cplx* twt = s_tw_t + frm * kG8BufCplx;                            // W128^((l + 48 frm) k1) at [k1 * 9 + l]
     const int per_sess = n_frames - first_frame;
     const double exp_pi = kExpPi;                                           // exp(angle(-1 + 0j))
     const long long n_pairs = (n_items + 1) >> 1;
@@ -137,50 +167,60 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
         const int k = first_frame + (int)(item - (long long)sess * per_sess);
         const long long frame = (long long)sess * n_frames + k;
 
-        // magnitudes of spectral frame k-1+frm at bins 0..128, and the initial waveform
+        // Set-up, written as ROLLED loops: straight-line it was 36 KB of code run once per block, which together with the 27 KB
+        // iteration loop overflowed the 32 KB instruction cache level (no_instruction stalls: 7 % of the kernel's samples).
+        // magnitudes of spectral frame k-1+frm at bins 0..128: exp() once per mel coefficient, then the 2-tap inverse mel matrix
         {
             const double* lm = logmel + (frame - 1 + frm) * n_mels;
             if (n_mels <= kG8MelMax) {
-                // exp() once per mel coefficient (40 per frame) instead of once per inverse-mel tap (258 per frame): the values
-                // sit in the tail of the block's buffer, which the 480-sample waveform does not use
-                double* em = x + kBlk + frm * kG8MelMax;
+#pragma unroll 1
                 for (int m = l8; m < n_mels; m += 8) em[m] = exp(lm[m]);
                 __syncwarp();
+#pragma unroll 2
                 for (int b = l8; b < kBins; b += 8) {
-                    const double w0 = tab.inv_w[b * 2], w1 = tab.inv_w[b * 2 + 1];
-                    double v = 0.0;
-                    if (w0 != 0.0) v = em[tab.inv_idx[b * 2]] * w0;
-                    if (w1 != 0.0) v = fma(em[tab.inv_idx[b * 2 + 1]], w1, v);
+                    const double2 w = s_inv_w[b];
+                    const int2 id = s_inv_i[b];
+                    const double e0 = em[id.x], e1 = em[id.y];
+                    double v = (w.x != 0.0) ? e0 * w.x : 0.0;
+                    v = (w.y != 0.0) ? fma(e1, w.y, v) : v;
                     v = isfinite(v) ? v : 0.0;                              // MelFilterBank.makeNormal
-                    g8_store_mag(ws.S[blk][frm], b, v);
+                    g8_store_mag(Sw, b, v);
                 }
             } else {
-                for (int b = l8; b < kBins; b += 8) g8_store_mag(ws.S[blk][frm], b, mel_magnitude(lm, tab.inv_idx, tab.inv_w, b));
+                for (int b = l8; b < kBins; b += 8) g8_store_mag(Sw, b, mel_magnitude(lm, tab.inv_idx, tab.inv_w, b));
             }
+        }
+        // the initial waveform: into the (still unused) transposition space, then into the register slots
+        {
+            double* xs = ws.xb[blk];
             const int l16 = lane & 15;
-            for (int i = l16; i < kBlk; i += 16)
-                x[i] = noise ? noise[frame * kBlk + i] : uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)i);
+            if (noise) {
+                const double2* src = reinterpret_cast<const double2*>(noise + frame * kBlk);
+#pragma unroll 1
+                for (int i = l16; i < kBlk / 2; i += 16) reinterpret_cast<double2*>(xs)[i] = src[i];
+            } else {
+#pragma unroll 1
+                for (int i = l16; i < kBlk; i += 16) xs[i] = uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)i);
+            }
         }
         __syncwarp();
-
-#pragma unroll 1
-        for (int it = 0; it < iters; ++it) {
-            cplx v[16];
-            // ---- analysis: window + pack (z[n] = x[o+2n] w[2n] + i x[o+2n+1] w[2n+1]), n = l8 + 8m ---------------
-            {
-                const double* xo = x + frm * kHop;
+        cplx v[16];
 #pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    const int n = l8 + 8 * m;
-                    const double2 xv = *reinterpret_cast<const double2*>(xo + 2 * n);
-                    const double2 wv = *reinterpret_cast<const double2*>(s_window + 2 * n);
-                    v[m] = cplx{xv.x * wv.x, xv.y * wv.y};
-                }
-            }
+        for (int s = 0; s < 16; ++s) {
+            const int p = (s < 10 ? pos_lo : pos_hi) + 16 * s;
+            const double2 xv = *reinterpret_cast<const double2*>(ws.xb[blk] + p);
+            const double2 wv = (s < 10 ? win_lo : win_hi)[8 * s];
+            v[s] = iters > 0 ? cplx{xv.x * wv.x, xv.y * wv.y} : cplx{xv.x, xv.y};
+        }
+        __syncwarp();                                                        // magnitudes visible; the scratch is dead
+
+        if (iters > 0) {
+#pragma unroll 1
+        for (int it = 0;; ++it) {
+            // ---- analysis: v = windowed packed frame ----------------------------------------------------------------
             dft16(v);
 #pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) v[pos16(k1)] = cmul(v[pos16(k1)], s_tw_t[k1 * kG8RowStride + l8]);
-            __syncwarp();                                                    // every lane has read x: its space becomes buf
+            for (int k1 = 1; k1 < 16; ++k1) v[pos16(k1)] = cmul(v[pos16(k1)], twt[k1 * kG8RowStride + l8]);
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) buf[k1 * kG8RowStride + l8] = v[pos16(k1)];
             __syncwarp();
@@ -201,24 +241,46 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                 V[i] = csel(lane0, ra[pos8(4 + i)], rb[pos8(i)]);
                 V[4 + i] = rb[pos8(4 + i)];
             }
+            // (A) split: X[kk] = E + O, X[128 - kk] = conj(E - O): the partner's twiddle w[128 - kk] = -conj(w[kk]) (the host
+            // table is built with that symmetry) makes its products the first one's, negated
+            double re[16], im[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int kk = lane0 ? (i < 4 ? 8 + 16 * i : 16 * (i - 3)) : l8 + 16 * i;
-                cplx B = V[7 - i];
-                // partner twiddle w[128 - kk] = -conj(w[kk]) (the host table is built with that symmetry)
+                const cplx w = s_tw_full[kk];
+                const cplx A = U[i], B = V[7 - i];
+                const cplx d1 = cplx{A.x - B.x, A.y + B.y}, t1 = cmul(w, d1);
+                const double ex = 0.5 * (A.x + B.x), ey = 0.5 * (A.y - B.y);
+                re[2 * i] = fma(0.5, t1.y, ex);      im[2 * i] = fma(-0.5, t1.x, ey);
+                re[2 * i + 1] = fma(-0.5, t1.y, ex); im[2 * i + 1] = fma(-0.5, t1.x, -ey);
+            }
+            // (B) exp(angle) of the 16 bins, four at a time
+            double ea[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const Ea4 e = exp_angle4_call(s_ea, im[4 * g], re[4 * g], im[4 * g + 1], re[4 * g + 1], im[4 * g + 2], re[4 * g + 2],
+                                              im[4 * g + 3], re[4 * g + 3]);
+                ea[4 * g] = e.a; ea[4 * g + 1] = e.b; ea[4 * g + 2] = e.c; ea[4 * g + 3] = e.d;
+            }
+            // (C) Z = S exp(angle X) (real, quirk Q1) and the inverse split, stored conjugated
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kk = lane0 ? (i < 4 ? 8 + 16 * i : 16 * (i - 3)) : l8 + 16 * i;
                 const cplx w = s_tw_full[kk];
                 const bool upper = !lane0 && i >= 4;                         // kk > 64: the pair sits at 128 - kk, swapped
-                const double2 sp = *reinterpret_cast<const double2*>(Sg + 2 * (upper ? kHalf - kk : kk));
-                g8_pair(s_ea, U[i], B, w, cplx{0.0 - w.x, w.y}, upper ? sp.y : sp.x, upper ? sp.x : sp.y);      // 0.0 - x: no -0.0 at the quadrant point
-                if (i != 7) V[7 - i] = B;                                    // pair 7 of lane 0 is the self-pair (64, 64): V[0] unused
-                else V[0] = lane0 ? V[0] : B;
+                const double2 sp = *reinterpret_cast<const double2*>(Sw + 2 * (upper ? kHalf - kk : kk));
+                const double z1 = (upper ? sp.y : sp.x) * ea[2 * i], z2 = (upper ? sp.x : sp.y) * ea[2 * i + 1];
+                const double sm = z1 + z2, df = z1 - z2;
+                const double yi = -(w.x * df);
+                U[i] = cplx{fma(w.y, df, sm), yi};
+                V[7 - i] = cplx{fma(w.y, -df, sm), yi};                      // pair 7 of lane 0 is the self-pair (64, 64): its V[0] is unused
             }
             cplx zdcny;
             {
                 // DC and Nyquist are real with imag = +0.0 in numpy: angle is 0 or pi
                 const double xdc = dc.x + dc.y, xny = dc.x - dc.y;
-                const double zdc = Sg[0] * ((xdc < 0.0 || (xdc == 0.0 && signbit(xdc))) ? exp_pi : 1.0);
-                const double zny = Sg[1] * ((xny < 0.0 || (xny == 0.0 && signbit(xny))) ? exp_pi : 1.0);
+                const double zdc = Sw[0] * ((xdc < 0.0 || (xdc == 0.0 && signbit(xdc))) ? exp_pi : 1.0);
+                const double zny = Sw[1] * ((xny < 0.0 || (xny == 0.0 && signbit(xny))) ? exp_pi : 1.0);
                 zdcny = cplx{zdc + zny, -(zdc - zny)};
             }
             // back to rows (natural k2 order for the next transform)
@@ -237,46 +299,39 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
             __syncwarp();                                                    // all row reads of buf are done
 #pragma unroll
             for (int l = 0; l < 8; ++l) {
-                const cplx ga = l == 0 ? ia[pos8(0)] : cmul(ia[pos8(l)], s_tw_t[row_a * kG8RowStride + l]);
-                const cplx gb = l == 0 ? ib[pos8(0)] : cmul(ib[pos8(l)], s_tw_t[row_b * kG8RowStride + l]);
-                buf[row_a * kG8RowStride + l] = ga;
-                buf[row_b * kG8RowStride + l] = gb;
+                // l = 0: 1 for frame 0, W16^(6 k1) for frame 1
+                buf[row_a * kG8RowStride + l] = cmul(ia[pos8(l)], twt[row_a * kG8RowStride + l]);
+                buf[row_b * kG8RowStride + l] = cmul(ib[pos8(l)], twt[row_b * kG8RowStride + l]);
             }
             __syncwarp();
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) v[k1] = buf[k1 * kG8RowStride + l8];
-            dft16(v);                                                        // conj(x~[l8 + 8m]) at v[pos16(m)]
-            __syncwarp();                                                    // buf is dead: the space becomes x again
-            // ---- synthesis: x = irfft(Z0) w at 0  (+)  irfft(Z1) w at 160; nothing reaches [416, 480) ------------------
-            if (frm == 0) {
-#pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    const int n = l8 + 8 * m;
-                    const double2 wv = *reinterpret_cast<const double2*>(s_window + 2 * n);
-                    *reinterpret_cast<double2*>(x + 2 * n) = make_double2(v[pos16(m)].x * wv.x, -v[pos16(m)].y * wv.y);
-                }
-            }
-            __syncwarp();
-            if (frm == 1) {
-#pragma unroll
-                for (int m = 0; m < 16; ++m) {                               // frame 0 first: the overlap is (0 + r0) + r1
-                    const int n = l8 + 8 * m, p = 2 * n;
-                    const double2 wv = *reinterpret_cast<const double2*>(s_window + p);
-                    const double r0 = v[pos16(m)].x * wv.x, r1 = -v[pos16(m)].y * wv.y;
-                    double2 cur = *reinterpret_cast<const double2*>(x + kHop + p);
-                    cur.x = (p < kFft - kHop) ? cur.x + r0 : r0;
-                    cur.y = (p + 1 < kFft - kHop) ? cur.y + r1 : r1;
-                    *reinterpret_cast<double2*>(x + kHop + p) = cur;
-                }
-#pragma unroll
-                for (int i = 0; i < (kBlk - kHop - kFft) / 8; ++i) x[kHop + kFft + l8 + 8 * i] = 0.0;
-            }
-            __syncwarp();
+            dft16(v);                                                        // conj(x~) of slot s at v[pos16(s)]
+            __syncwarp();                                                    // column reads done before the next stores
+            if (it + 1 >= iters) break;
+            g8_synthesis<true>(v, win_lo, win_hi);
+        }
+        g8_synthesis<false>(v, win_lo, win_hi);
         }
         if (valid) {
+            // v = the block's samples: frame 0 owns [0, 256), frame 1 [256, 416); [416, 480) = 0 after any iteration
             const long long row = ring_len ? ((ring_base + k) & (ring_len - 1)) : frame;
-            const int l16 = lane & 15;
-            for (int i = l16; i < kBlk; i += 16) blocks[row * kBlk + i] = x[i];
+#pragma unroll
+            for (int s = 0; s < 16; ++s)
+                if (!f1 || s < 10) *reinterpret_cast<double2*>(blocks + row * kBlk + (s < 10 ? pos_lo : pos_hi) + 16 * s) = make_double2(v[s].x, v[s].y);
+            if (f1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int p = kHop + kFft + 2 * l8 + 16 * i;             // 416 + ...
+                    double2 t = make_double2(0.0, 0.0);
+                    if (iters == 0) {
+                        if (noise) t = *reinterpret_cast<const double2*>(noise + frame * kBlk + p);
+                        else t = make_double2(uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)p),
+                                              uniform01(seed, (unsigned long long)(ring_base + frame), (unsigned)p + 1));
+                    }
+                    *reinterpret_cast<double2*>(blocks + row * kBlk + p) = t;
+                }
+            }
         }
         __syncwarp();
     }

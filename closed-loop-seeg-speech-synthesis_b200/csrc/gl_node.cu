@@ -44,13 +44,16 @@ __device__ __noinline__ double mel_magnitude(const double* lm, const int* inv_id
     return isfinite(v) ? v : 0.0;                                           // MelFilterBank.makeNormal
 }
 
-// out-of-line copy of the pair evaluation: one body in the instruction cache, called 4 times per iteration
-__device__ __noinline__ double2 exp_angle_pair_call(const double* s_tab, double im1, double re1, double im2, double re2) {
-    double a, b;
-    exp_angle_pair(s_tab, im1, re1, im2, re2, a, b);
-    return make_double2(a, b);
+// out-of-line copy of the four-wide evaluation: one body in the instruction cache, called 4 times per iteration (inlined
+// four-, eight- and sixteen-wide it measured 29.1 / 30.4 / 35.6 ms per 1.92 M blocks against 28.8 ms: spills)
+struct Ea4 { double a, b, c, d; };
+__device__ __noinline__ Ea4 exp_angle4_call(const double* s_tab, double im0, double re0, double im1, double re1, double im2,
+                                            double re2, double im3, double re3) {
+    const double im[4] = {im0, im1, im2, im3}, re[4] = {re0, re1, re2, re3};
+    double out[4];
+    exp_angle_n<4>(s_tab, im, re, out);
+    return Ea4{out[0], out[1], out[2], out[3]};
 }
-
 
 }  // namespace sgs
 #include "gl_blocks8.cuh"
@@ -285,9 +288,10 @@ __global__ void k_exp_angle(const double* __restrict__ im, const double* __restr
     __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        double a, b;
-        exp_angle_pair(s_tab, im[i], re[i], im[i], re[i], a, b);
-        out[i] = a;
+        const double vi[1] = {im[i]}, vr[1] = {re[i]};
+        double o[1];
+        exp_angle_n<1>(s_tab, vi, vr, o);
+        out[i] = o[0];
     }
 }
 
@@ -308,15 +312,17 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
     const long long n_items = (long long)n_sessions * (n_frames - first_frame);
     if (n_items <= 0) return SGS_OK;
     ProfScope ps(kProfGlBlocks, st);
-    // 8 warps x 2 CTAs per SM: 128 registers per thread and 113 KB of shared memory per CTA (16 resident warps = 32 blocks)
-    constexpr int W = 8;
-    const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kG8SLen + kG8BufCplx) + sizeof(double) * kEaTabLen + sizeof(G8WarpSmem) * W;
-    static unsigned long long optin = 0;
-    SGS_CUDA(smem_optin(k_gl_blocks8<W, 2>, smem, &optin));
+    // one CTA of 16 warps per SM: 128 registers per thread = the whole register file, 226 KB of shared memory (the tables once +
+    // 13.4 KB per warp: 32 blocks in flight per SM)
+    constexpr int W = 16;
+    const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kG8SLen + 2 * kG8BufCplx) + (sizeof(double2) + sizeof(int2)) * kG8SLen +
+                        sizeof(double) * kEaTabLen + sizeof(G8WarpSmem) * W;
     const long long n_pairs = (n_items + 1) / 2, want = (n_pairs + W - 1) / W;
-    const int grid = (int)(want < 148LL * 2 * 8 ? want : 148LL * 2 * 8);
+    const int grid = (int)(want < 148LL * 4 ? want : 148LL * 4);
     const G8Tables t8{tab.window, tab.tw_t, tab.tw_full, tab.inv_idx, tab.inv_w};
-    k_gl_blocks8<W, 2><<<grid, W * 32, smem, st>>>(logmel, noise, seed, blocks, t8, n_frames, n_mels, first_frame, iters, n_items,
+    static unsigned long long optin = 0;
+    SGS_CUDA(smem_optin(k_gl_blocks8<W, 1>, smem, &optin));
+    k_gl_blocks8<W, 1><<<grid, W * 32, smem, st>>>(logmel, noise, seed, blocks, t8, n_frames, n_mels, first_frame, iters, n_items,
                                                    ring_base, ring_len);
     SGS_LAUNCHED();
     SGS_CUDA(cudaGetLastError());

@@ -68,7 +68,7 @@ constexpr int kBlockRing = 32;          // >= kMaxFramesPerPush + 4: a push writ
 struct GlNodeTables {                   // device pointers, built once per node configuration
     const double* window;               // blackman(256)
     const cplx* tw_full;                // exp(-2 pi i k / 256), k <= 128
-    const cplx* tw_t;                   // [16][9] W128^(l k1) (register-FFT kernel, gl_blocks8.cuh)
+    const cplx* tw_t;                   // [2][16][9] W128^((l + 48 f) k1) (register-FFT kernel, gl_blocks8.cuh)
     const int* inv_idx;                 // [129][2] mel index of each inverse-mel tap
     const double* inv_w;                // [129][2] weight (0 where unused)
 };

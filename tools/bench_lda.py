@@ -19,7 +19,7 @@ if __name__ == '__main__':
     W = int(sys.argv[2]) if len(sys.argv) > 2 else 60000
     _lib.ensure_init(0)
     rng = np.random.default_rng(7)
-    model, select, medians = bench.random_model(rng, 5 * 128)
+    model, select, medians = bench.trained_model()
     dec = LdaDecoder(model, select, medians)
     torch.manual_seed(0)
     lp = torch.randn((S, W, 128), dtype=torch.float64, device='cuda') * 0.6 + 8.0

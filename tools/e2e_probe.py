@@ -20,7 +20,7 @@ if __name__ == '__main__':
     _lib.ensure_init(0)
     torch.cuda.set_device(0)
     rng = np.random.default_rng(7)
-    model, select, medians = bench.random_model(rng, 5 * bench.N_CH)
+    model, select, medians = bench.trained_model()
     decoder = dec_mod.OfflineDecoder(model, medians, select, bench.SR, gl_norm=10, packet_size=64)
     T = int(bench.SR * bench.DUR)
     xh = torch.empty((S, T, bench.N_CH), dtype=torch.float32).pin_memory()
