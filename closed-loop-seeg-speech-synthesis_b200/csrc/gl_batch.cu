@@ -11,19 +11,19 @@
 // The reference also transforms 5x more STFT frames than it uses and the last 5 spectral frames never reach the
 // output; neither is reproduced as work, both are reproduced as results.
 //
-// One CTA per utterance, 13 warps, one frame per warp per round.  Frames are processed in ascending order, which
-// makes the update in place: hop segment h of x is final once frame h is done, and no later frame of the same
-// iteration reads it.  The windowed inverse transforms of the last 18 frames sit in a shared-memory ring so each
-// output sample is summed over its (up to 5) contributing frames in the reference's accumulation order; a frame's
-// ring slot is free until its own result lands there, so it doubles as the second buffer of the Stockham stages.
+// One launch per iteration (the waveform ping-pongs between two buffers), one CTA per utterance - or per range of hop
+// segments when there are few utterances - see k_gl_batch_iter.
 #include <math.h>
 #include "kernels.cuh"
 
 namespace sgs {
 
-constexpr int kBW = 13;                 // warps per CTA (195 frames reach the output at T = 200: 15 full rounds)
 constexpr int kN = 800, kM = 400, kHopB = 160, kBinsB = 401, kOverlap = 5;
-constexpr int kRingB = kBW + kOverlap;  // 18 slots
+constexpr int kBF = 8;                  // frames per round
+constexpr int kBT = kBF * 20;           // threads per CTA: one 20-point transform per thread and pass
+constexpr int kRow = 21;                // row stride of a frame buffer (20 complex entries + 1 pad: rows and columns conflict-free)
+constexpr int kBufC = 20 * kRow;        // complex entries per frame buffer
+constexpr int kCarry = kOverlap - 1;    // hop segments that still receive contributions from later rounds
 
 // X / |X| without sqrt and divisions: reciprocal square root seed and two Newton steps (<= 2 ulp);
 // 0 -> (1, 0) as angle(0) = 0.  |X|^2 outside [2^-900, 2^900] takes the plain route.
@@ -43,110 +43,193 @@ __device__ __forceinline__ cplx unit_phase(cplx X) {
     return cplx{X.x * r, X.y * r};
 }
 
-__global__ void __launch_bounds__(kBW * 32)
-k_gl_batch(const double* __restrict__ logmel /*[B][T][n_mels]*/, double* __restrict__ x /*[B][x_len] in: noise, out: waveform*/,
-           const GlBatchTables tab, int T, int n_mels, int iters, long long x_len) {
+// 20-point DFT in registers by the prime-factor map (4 x 5, no twiddles between the two passes):
+//   g[a][b] = v[(5 a + 4 b) % 20];  5-point DFTs along b, 4-point DFTs along a;  X[(5 ka + 16 kb) % 20] = g[ka][kb]
+// so X[k] ends in v[pos20(k)], pos20(k) = (5 (k % 4) + 4 (k % 5)) % 20.  224 fp64 operations.
+__device__ __forceinline__ constexpr int pos20(int k) { return (5 * (k % 4) + 4 * (k % 5)) % 20; }
+template <int SIGN>
+__device__ __forceinline__ void dft20(cplx (&v)[20]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        cplx t[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) t[b] = v[(5 * a + 4 * b) % 20];
+        Butterfly<5, SIGN>::run(t);
+#pragma unroll
+        for (int b = 0; b < 5; ++b) v[(5 * a + 4 * b) % 20] = t[b];
+    }
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        cplx t[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) t[a] = v[(5 * a + 4 * b) % 20];
+        Butterfly<4, SIGN>::run(t);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) v[(5 * a + 4 * b) % 20] = t[a];
+    }
+}
+
+// magnitudes S = fromLogMels(spectrogram) of the frames the inverse uses: [utterance][frame < T-5][401]
+__global__ void k_gl_batch_mag(const double* __restrict__ logmel, const int* __restrict__ inv_idx, const double* __restrict__ inv_w,
+                               double* __restrict__ S, int T, int n_used, int n_mels) {
+    __shared__ double ex[64];
+    const int n = blockIdx.x, u = blockIdx.y;
+    const double* lm = logmel + ((long long)u * T + n) * n_mels;
+    for (int m = threadIdx.x; m < n_mels; m += blockDim.x) ex[m] = exp(lm[m]);
+    __syncthreads();
+    double* out = S + ((long long)u * n_used + n) * kBinsB;
+    for (int b = threadIdx.x; b < kBinsB; b += blockDim.x) {
+        const double w0 = inv_w[b * 2], w1 = inv_w[b * 2 + 1];
+        double v = 0.0;
+        if (w0 != 0.0) v = ex[inv_idx[b * 2]] * w0;
+        if (w1 != 0.0) v = fma(ex[inv_idx[b * 2 + 1]], w1, v);
+        out[b] = isfinite(v) ? v : 0.0;                                     // MelFilterBank.makeNormal
+    }
+}
+
+// One Griffin-Lim iteration of hop segments [c R, (c+1) R) of utterance u = blockIdx.y: xin -> xout.
+//
+// The 800-point real transform is a 400-point complex one laid out as 20 x 20, and a thread holds one 20-point transform in
+// registers: pass 1 (thread = (frame, l)) transforms z[l + 20 m] over m and applies W400^(l k1), pass 2 (thread = (frame,
+// k1)) transforms over l; bin k1 + 20 k2 then sits at [k1][k2] of the frame's shared-memory buffer, which every pass
+// updates in place (a thread writes exactly the 20 entries it read).  The real-FFT split, the phase projection
+// Z = S X / |X| and the inverse split run per bin pair (k, 400 - k); the inverse mirrors the two passes.  A round handles
+// kBF consecutive frames; their windowed outputs are summed per hop segment in ascending frame order - the order of the
+// reference's `re[i:i+800] += ...` loop - on top of the partial sums the earlier rounds left for the 4 segments that were
+// still open (`carry`), so no frame buffer outlives its round.  The first version ran four Stockham stages per transform
+// through shared memory with 13 frames in flight per SM: 22 % of the FP64 pipe (profiles/ncu_gl_blocks8_r01b.txt).
+__global__ void __launch_bounds__(kBT, 3)
+k_gl_batch_iter(const double* __restrict__ xin, long long in_stride, double* __restrict__ xout, long long out_stride,
+                const double* __restrict__ S, const GlBatchTables tab, int T, int n_used, int seg_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_window = reinterpret_cast<double*>(smem_raw);                 // [800]
-    cplx* s_tw_half = reinterpret_cast<cplx*>(s_window + kN);               // [400]
-    cplx* s_tw_full = s_tw_half + kM;                                       // [401] (+1 pad)
-    double* s_ring = reinterpret_cast<double*>(s_tw_full + kBinsB + 1);     // [18][800]
-    cplx* s_work = reinterpret_cast<cplx*>(s_ring + kRingB * kN);           // per warp: a[400]
-    double* s_exp = reinterpret_cast<double*>(s_work + kBW * kM);           // per warp: exp(logmel) [n_mels <= 64]
-    for (int i = threadIdx.x; i < kN; i += blockDim.x) s_window[i] = tab.window[i];
-    fft400_stage_tables(s_tw_half, tab.tw_half);                             // [395] per-stage twiddles
-    for (int i = threadIdx.x; i < kBinsB; i += blockDim.x) s_tw_full[i] = tab.tw_full[i];
+    cplx* s_buf = reinterpret_cast<cplx*>(smem_raw);                        // [kBF][kBufC]
+    double* s_carry = reinterpret_cast<double*>(s_buf + kBF * kBufC);       // [kCarry][160]
+    cplx* s_twt = reinterpret_cast<cplx*>(s_carry + kCarry * kHopB);        // [20][20] W400^(l k1) (symmetric)
+    double2* s_win2 = reinterpret_cast<double2*>(s_twt + 400);              // [400] window pairs (w[2n], w[2n+1])
+    cplx* s_twf = reinterpret_cast<cplx*>(s_win2 + kM);                     // [201] exp(-2 pi i k / 800)
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 400; i += kBT) s_twt[i] = tab.tw_half[((i / 20) * (i % 20)) % kM];
+    for (int i = tid; i < kM; i += kBT) s_win2[i] = make_double2(tab.window[2 * i], tab.window[2 * i + 1]);
+    for (int i = tid; i <= kM / 2; i += kBT) s_twf[i] = tab.tw_full[i];
+    for (int i = tid; i < kCarry * kHopB; i += kBT) s_carry[i] = 0.0;
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    cplx* a = s_work + (size_t)warp * kM;
-    double* ex = s_exp + warp * 64;
-    double* xu = x + (long long)blockIdx.x * x_len;
-    const double* lm_u = logmel + (long long)blockIdx.x * T * n_mels;
-    const int n_used = T - kOverlap;                                        // frames that reach the output
+    const int u = blockIdx.y;
+    const int h0 = blockIdx.x * seg_per_cta, h1 = min(h0 + seg_per_cta, T);
+    const double* xu = xin + (long long)u * in_stride;
+    double* xo = xout + (long long)u * out_stride;
+    const double* Su = S + (long long)u * n_used * kBinsB;
+    const int n_lim = min(n_used, h1);                                      // frames >= h1 only reach segments of the next range
+    const int f = tid / 20, l = tid - f * 20;                               // frame of the round, row / column index
+    cplx* A = s_buf + f * kBufC;
     constexpr double scale = 1.0 / kN;
 
-    for (int it = 0; it < iters; ++it) {
-        for (int g0 = 0; g0 < T; g0 += kBW) {                               // rounds of kBW frames, ascending
-            const int n = g0 + warp;
-            if (n < n_used) {
-                double* slot = s_ring + (size_t)(n % kRingB) * kN;
-                cplx* b = reinterpret_cast<cplx*>(slot);                    // scratch until the frame's result is stored
-                for (int m = lane; m < n_mels; m += 32) ex[m] = exp(lm_u[(long long)n * n_mels + m]);
-                const double* xin = xu + (long long)n * kHopB;
-                for (int i = lane; i < kM; i += 32) {
-                    const double2 xv = *reinterpret_cast<const double2*>(xin + 2 * i);
-                    const double2 wv = *reinterpret_cast<const double2*>(s_window + 2 * i);
-                    a[i] = cplx{xv.x * wv.x, xv.y * wv.y};
-                }
-                __syncwarp();
-                fft400<-1>(a, b, s_tw_half, lane);
-                // real-FFT split, phase projection Z = S * X/|X|, and the inverse split, bin pairs (k, 400-k) together
-                for (int k = lane; k <= kM / 2; k += 32) {
-                    const int k2 = kM - k;
-                    cplx Xk, Xk2;
-                    if (k == 0) {
-                        Xk = cplx{a[0].x + a[0].y, 0.0};                    // DC
-                        Xk2 = cplx{a[0].x - a[0].y, 0.0};                   // Nyquist (k2 = 400)
-                    } else {
-                        const cplx A = a[k], B = cconj(a[k2]);
-                        const cplx d = csub(A, B);
-                        const cplx t1 = cmul(s_tw_full[k], d);
-                        Xk = cplx{0.5 * (A.x + B.x) + 0.5 * t1.y, 0.5 * (A.y + B.y) - 0.5 * t1.x};
-                        // X[400-k] from the same pair: A' = a[k2], B' = conj(a[k])
-                        const cplx A2 = a[k2], B2 = cconj(a[k]);
-                        const cplx d2 = csub(A2, B2);
-                        const cplx t2 = cmul(s_tw_full[k2], d2);
-                        Xk2 = cplx{0.5 * (A2.x + B2.x) + 0.5 * t2.y, 0.5 * (A2.y + B2.y) - 0.5 * t2.x};
-                    }
-                    auto project = [&](cplx X, int bin) -> cplx {
-                        const double w0 = tab.inv_w[bin * 2], w1 = tab.inv_w[bin * 2 + 1];
-                        double S = 0.0;
-                        if (w0 != 0.0) S = ex[tab.inv_idx[bin * 2]] * w0;
-                        if (w1 != 0.0) S = fma(ex[tab.inv_idx[bin * 2 + 1]], w1, S);
-                        if (!isfinite(S)) S = 0.0;
-                        const cplx u = unit_phase(X);
-                        return cplx{S * u.x, S * u.y};
-                    };
-                    const cplx Zk = project(Xk, k), Zk2 = project(Xk2, k2);
-                    // irfft ignores the imaginary parts of the DC and Nyquist bins
-                    if (k == 0) {
-                        a[0] = cplx{Zk.x + Zk2.x, Zk.x - Zk2.x};
-                    } else {
-                        // Zin[k] = (A + B) + i e^{+i th_k} (A - B) with A = Z[k], B = conj(Z[400-k]); same for 400-k
-                        const cplx A = Zk, B = cconj(Zk2);
-                        const cplx s1 = cadd(A, B), d1 = csub(A, B);
-                        const cplx w = s_tw_full[k];                        // (cos, -sin)
-                        // i e^{i th} d = i (cos + i sin)(dx + i dy) = (-sin dx - cos dy) + i (cos dx - sin dy)
-                        const cplx r1 = cplx{fma(w.y, d1.x, -w.x * d1.y), fma(w.x, d1.x, w.y * d1.y)};
-                        const cplx A2 = Zk2, B2 = cconj(Zk);
-                        const cplx s2 = cadd(A2, B2), d2 = csub(A2, B2);
-                        const cplx w2 = s_tw_full[k2];
-                        const cplx r2 = cplx{fma(w2.y, d2.x, -w2.x * d2.y), fma(w2.x, d2.x, w2.y * d2.y)};
-                        a[k] = cadd(s1, r1);
-                        if (k2 != k) a[k2] = cadd(s2, r2);
-                    }
-                }
-                __syncwarp();
-                fft400<+1>(a, b, s_tw_half, lane);
-                for (int i = lane; i < kM; i += 32) {
-                    const double2 wv = *reinterpret_cast<const double2*>(s_window + 2 * i);
-                    const cplx v = a[i];
-                    *reinterpret_cast<double2*>(slot + 2 * i) = make_double2((v.x * scale) * wv.x, (v.y * scale) * wv.y);
-                }
+    for (int g0 = max(h0 - kCarry, 0); g0 < h1; g0 += kBF) {
+        const int n = g0 + f;
+        const bool live = n < n_lim;
+        cplx v[20];
+        // ---- pass 1: window + pack z[j] = x[2j] w[2j] + i x[2j+1] w[2j+1], j = l + 20 m; transform over m; twiddle ----------
+        if (live) {
+            const double2* x2 = reinterpret_cast<const double2*>(xu + (long long)n * kHopB) + l;
+#pragma unroll
+            for (int m = 0; m < 20; ++m) {
+                const double2 xv = x2[20 * m], wv = s_win2[l + 20 * m];
+                v[m] = cplx{xv.x * wv.x, xv.y * wv.y};
             }
-            __syncthreads();
-            // hop segments g0 .. g0+7 are final now: sum their contributing frames in ascending order
-            for (int idx = threadIdx.x; idx < kBW * kHopB; idx += blockDim.x) {
-                const int h = g0 + idx / kHopB, j = idx - (idx / kHopB) * kHopB;
-                if (h >= T) break;
-                double acc = 0.0;
-                for (int nn = h - (kOverlap - 1); nn <= h; ++nn)
-                    if (nn >= 0 && nn < n_used) acc += s_ring[(size_t)(nn % kRingB) * kN + (h - nn) * kHopB + j];
-                xu[(long long)h * kHopB + j] = acc;
-            }
-            __syncthreads();
+            dft20<-1>(v);
+            A[l] = v[pos20(0)];
+#pragma unroll
+            for (int k1 = 1; k1 < 20; ++k1) A[k1 * kRow + l] = cmul(v[pos20(k1)], s_twt[k1 * 20 + l]);
         }
+        __syncthreads();
+        // ---- pass 2: row k1 = l, transform over the column index; bin k1 + 20 k2 -> [k1][k2] ---------------------------------
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 20; ++j) v[j] = A[l * kRow + j];
+            dft20<-1>(v);
+#pragma unroll
+            for (int k2 = 0; k2 < 20; ++k2) A[l * kRow + k2] = v[pos20(k2)];
+        }
+        __syncthreads();
+        // ---- bin pairs (k, 400 - k), k = 1..200: split, Z = S X / |X|, inverse split -------------------------------------------
+        // with A = Zc[k], B = conj(Zc[400-k]), t = w_k (A - B):  X[k] = E + O, X[400-k] = conj(E - O),  E = (A + B)/2, O = -i t/2
+        // and back:  Zin[k] = s + r, Zin[400-k] = conj(s - r),  s = Z[k] + conj(Z[400-k]),  r = i conj(w_k) (Z[k] - conj(Z[400-k]))
+#pragma unroll 2
+        for (int p = tid; p < kBF * 200; p += kBT) {
+            const int fp = p / 200, k = 1 + (p - fp * 200), k2 = kM - k, np = g0 + fp;
+            if (np >= n_lim) continue;
+            cplx* Ap = s_buf + fp * kBufC;
+            const int ia = (k % 20) * kRow + k / 20, ib = (k2 % 20) * kRow + k2 / 20;
+            const double sk = Su[(long long)np * kBinsB + k], sk2 = Su[(long long)np * kBinsB + k2];
+            const cplx Za = Ap[ia], Zb = Ap[ib], w = s_twf[k];
+            const cplx d = cplx{Za.x - Zb.x, Za.y + Zb.y}, t = cmul(w, d);
+            const double ex = 0.5 * (Za.x + Zb.x), ey = 0.5 * (Za.y - Zb.y);
+            const cplx X1 = cplx{fma(0.5, t.y, ex), fma(-0.5, t.x, ey)};
+            const cplx X2 = cplx{fma(-0.5, t.y, ex), fma(-0.5, t.x, -ey)};
+            const cplx u1 = unit_phase(X1), u2 = unit_phase(X2);
+            const cplx Z1 = cplx{sk * u1.x, sk * u1.y}, Z2 = cplx{sk2 * u2.x, sk2 * u2.y};
+            const cplx sm = cplx{Z1.x + Z2.x, Z1.y - Z2.y}, df = cplx{Z1.x - Z2.x, Z1.y + Z2.y};
+            // i e^{i th} df = i (cos + i sin)(dx + i dy) = (-sin dx - cos dy) + i (cos dx - sin dy), w = (cos, -sin)
+            const cplx r = cplx{fma(w.y, df.x, -w.x * df.y), fma(w.x, df.x, w.y * df.y)};
+            Ap[ia] = cplx{sm.x + r.x, sm.y + r.y};
+            if (k2 != k) Ap[ib] = cplx{sm.x - r.x, -(sm.y - r.y)};
+        }
+        if (tid < kBF && g0 + tid < n_lim) {
+            // DC and Nyquist are real: Z = S sign(X) (the reference's exp(1j * pi) has real part -1; irfft drops the imaginary parts)
+            cplx* Ap = s_buf + tid * kBufC;
+            const long long so = (long long)(g0 + tid) * kBinsB;
+            const cplx z0 = Ap[0];
+            const cplx ud = unit_phase(cplx{z0.x + z0.y, 0.0}), un = unit_phase(cplx{z0.x - z0.y, 0.0});
+            const double zd = Su[so] * ud.x, zn = Su[so + kM] * un.x;
+            Ap[0] = cplx{zd + zn, zd - zn};
+        }
+        __syncthreads();
+        // ---- inverse pass A: row k1 = l over k2, twiddle conj(W400^(l' k1)); inverse pass B: column l over k1 -------------------
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 20; ++j) v[j] = A[l * kRow + j];
+            dft20<+1>(v);
+            A[l * kRow] = v[pos20(0)];
+#pragma unroll
+            for (int j = 1; j < 20; ++j) {
+                const cplx w = s_twt[j * 20 + l];                            // = W400^(j k1), the table is symmetric
+                A[l * kRow + j] = cmul(v[pos20(j)], cplx{w.x, -w.y});
+            }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int k1 = 0; k1 < 20; ++k1) v[k1] = A[k1 * kRow + l];
+            dft20<+1>(v);
+            // y[2j], y[2j+1] = Re, Im of the unnormalised inverse at j = l + 20 m, windowed: kept at [m][l]
+#pragma unroll
+            for (int m = 0; m < 20; ++m) {
+                const double2 wv = s_win2[l + 20 * m];
+                A[m * kRow + l] = cplx{(v[pos20(m)].x * scale) * wv.x, (v[pos20(m)].y * scale) * wv.y};
+            }
+        }
+        __syncthreads();
+        // ---- overlap-add: segments g0 .. g0+kBF-1 are final, the next 4 stay open ---------------------------------------------------
+        {
+            const int j = tid;                                               // sample within the hop (kBT == kHopB)
+            const double* Ad = reinterpret_cast<const double*>(s_buf);
+#pragma unroll
+            for (int sgm = 0; sgm < kBF + kCarry; ++sgm) {
+                const int h = g0 + sgm;
+                double acc = sgm < kCarry ? s_carry[sgm * kHopB + j] : 0.0;
+#pragma unroll
+                for (int d = kOverlap - 1; d >= 0; --d) {                    // ascending frame h - d
+                    const int fr = sgm - d;
+                    if (fr >= 0 && fr < kBF && g0 + fr < n_lim) {
+                        const int i = d * kHopB + j, jc = i >> 1;
+                        acc += Ad[(size_t)fr * (2 * kBufC) + 2 * ((jc / 20) * kRow + jc % 20) + (i & 1)];
+                    }
+                }
+                if (sgm < kBF) { if (h >= h0 && h < h1) xo[(long long)h * kHopB + j] = acc; }
+                else s_carry[(sgm - kBF) * kHopB + j] = acc;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -176,16 +259,49 @@ __global__ void k_scale_int16(const double* __restrict__ x, long long x_len, lon
 
 int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int n_utt, int T, int n_mels, int iters,
                  long long x_len, double* mx, short* pcm, cudaStream_t st) {
-    const size_t smem = sizeof(double) * kN + sizeof(cplx) * (kM + kBinsB + 1) + sizeof(double) * kRingB * kN +
-                        sizeof(cplx) * kBW * kM + sizeof(double) * kBW * 64;
-    static unsigned long long optin = 0;
-    SGS_CUDA(smem_optin(k_gl_batch, smem, &optin));
-    {
-        ProfScope ps(kProfGlBatch, st);
-        k_gl_batch<<<n_utt, kBW * 32, smem, st>>>(logmel, x, tab, T, n_mels, iters, x_len);
-    }
-    SGS_LAUNCHED();
+    static_assert(kBT == kHopB, "the overlap-add maps one thread to one sample of a hop");
     const long long n = (long long)T * kHopB;
+    const int n_used = T - kOverlap;
+    if (iters > 0) {
+        const size_t smem = sizeof(cplx) * (kBF * kBufC + 400 + kM / 2 + 1) + sizeof(double) * kCarry * kHopB + sizeof(double2) * kM;
+        static unsigned long long optin = 0;
+        SGS_CUDA(smem_optin(k_gl_batch_iter, smem, &optin));
+        // hop segments per CTA: whole utterances when there are enough of them to fill the device several times over, else
+        // ranges (each range re-computes the 4 frames before it, so no sum crosses a CTA)
+        int dev = 0, sms = 148;
+        SGS_CUDA(cudaGetDevice(&dev));
+        SGS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const long long slots = 3LL * sms;
+        int parts = 1, seg = T;
+        long long best = -1;
+        for (int want = 1; want <= 8; want *= 2) {
+            int sg = (T + want - 1) / want;
+            sg = (sg + 3) / kBF * kBF + kBF - kCarry;                        // segments + the 4 re-computed frames = whole rounds
+            if (want > 1 && sg < 3 * kBF) break;
+            const int np = (T + sg - 1) / sg;
+            const int rounds = np == 1 ? (T + kBF - 1) / kBF : (sg + kCarry + kBF - 1) / kBF;
+            const long long cost = (((long long)n_utt * np + slots - 1) / slots) * rounds;
+            if (best < 0 || cost < best) { best = cost; parts = np; seg = sg; }
+        }
+        double *y = nullptr, *S = nullptr;
+        SGS_CUDA(cudaMallocAsync((void**)&y, sizeof(double) * (size_t)n_utt * n, st));
+        SGS_CUDA(cudaMallocAsync((void**)&S, sizeof(double) * (size_t)n_utt * n_used * kBinsB, st));
+        k_gl_batch_mag<<<dim3(n_used, n_utt), 128, 0, st>>>(logmel, tab.inv_idx, tab.inv_w, S, T, n_used, n_mels);
+        SGS_LAUNCHED();
+        {
+            ProfScope ps(kProfGlBatch, st);
+            for (int it = 0; it < iters; ++it) {
+                const bool fwd = (it & 1) == 0;                              // x -> y on even iterations, y -> x on odd ones
+                k_gl_batch_iter<<<dim3(parts, n_utt), kBT, smem, st>>>(fwd ? x : y, fwd ? x_len : n, fwd ? y : x, fwd ? n : x_len, S, tab,
+                                                                       T, n_used, seg);
+                SGS_LAUNCHED();
+            }
+        }
+        if (iters & 1)
+            SGS_CUDA(cudaMemcpy2DAsync(x, sizeof(double) * x_len, y, sizeof(double) * n, sizeof(double) * n, n_utt, cudaMemcpyDeviceToDevice, st));
+        SGS_CUDA(cudaFreeAsync(y, st));
+        SGS_CUDA(cudaFreeAsync(S, st));
+    }
     k_absmax<<<n_utt, 256, 0, st>>>(x, x_len, n, mx);
     SGS_LAUNCHED();
     k_scale_int16<<<dim3(ceil_div(n, 256), n_utt), 256, 0, st>>>(x, x_len, n, mx, pcm);
