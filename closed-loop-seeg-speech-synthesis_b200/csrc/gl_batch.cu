@@ -11,9 +11,11 @@
 // The reference also transforms 5x more STFT frames than it uses and the last 5 spectral frames never reach the
 // output; neither is reproduced as work, both are reproduced as results.
 //
-// One launch per iteration (the waveform ping-pongs between two buffers), one CTA per utterance - or per range of hop
-// segments when there are few utterances - see k_gl_batch_iter.
+// One launch per iteration (the waveform ping-pongs between two buffers), three CTAs per SM, each working through an equal
+// run of 8-frame rounds of the utterance-major line of all rounds - see k_gl_batch_iter.
 #include <math.h>
+#include <stdlib.h>
+#include <algorithm>
 #include "kernels.cuh"
 
 namespace sgs {
@@ -23,6 +25,7 @@ constexpr int kBF = 8;                  // frames per round
 constexpr int kBT = kBF * 20;           // threads per CTA: one 20-point transform per thread and pass
 constexpr int kRow = 21;                // row stride of a frame buffer (20 complex entries + 1 pad: rows and columns conflict-free)
 constexpr int kBufC = 20 * kRow;        // complex entries per frame buffer
+constexpr int kPairsPerThread = kBF * 200 / kBT;   // bin pairs (k, 400 - k), k = 1..200, of the round's frames per thread
 constexpr int kCarry = kOverlap - 1;    // hop segments that still receive contributions from later rounds
 
 // X / |X| without sqrt and divisions: reciprocal square root seed and two Newton steps (<= 2 ulp);
@@ -87,7 +90,7 @@ __global__ void k_gl_batch_mag(const double* __restrict__ logmel, const int* __r
     }
 }
 
-// One Griffin-Lim iteration of hop segments [c R, (c+1) R) of utterance u = blockIdx.y: xin -> xout.
+// One Griffin-Lim iteration: xin -> xout.
 //
 // The 800-point real transform is a 400-point complex one laid out as 20 x 20, and a thread holds one 20-point transform in
 // registers: pass 1 (thread = (frame, l)) transforms z[l + 20 m] over m and applies W400^(l k1), pass 2 (thread = (frame,
@@ -98,9 +101,20 @@ __global__ void k_gl_batch_mag(const double* __restrict__ logmel, const int* __r
 // reference's `re[i:i+800] += ...` loop - on top of the partial sums the earlier rounds left for the 4 segments that were
 // still open (`carry`), so no frame buffer outlives its round.  The first version ran four Stockham stages per transform
 // through shared memory with 13 frames in flight per SM: 22 % of the FP64 pipe (profiles/ncu_gl_blocks8_r01b.txt).
+//
+// Work split: the rounds of all utterances form one line (utterance-major, `rpu` rounds per utterance) cut into runs of
+// `slots_per_cta`, one run per CTA.  With many utterances a run is exactly one utterance (4096 CTAs for config 4: the
+// hardware's dynamic CTA placement evens out the SMs; a perfectly even static split over one wave of CTAs measured 117.0 ms
+// against 112.1 ms, and splitting only the last utterances of the launch changed nothing - the few CTAs left at the end
+// run proportionally faster).  With fewer utterances than a few waves of CTAs the runs are equal shares of the line, so that
+// 512 utterances (config 4 over 8 GPUs) keep every SM busy: 15.4 ms against 16.6 ms in whole or quartered utterances.
+// A run that starts inside an utterance, at round r, owns its segments from 8 r + 4 on: it re-computes frames 8 r .. 8 r + 3,
+// which its predecessor also computes - in one extra, half-empty round - to finish segments 8 r .. 8 r + 3.  No sum crosses
+// a CTA and every sample is summed in the same order wherever the cuts fall, so the output does not depend on the batch.
 __global__ void __launch_bounds__(kBT, 3)
 k_gl_batch_iter(const double* __restrict__ xin, long long in_stride, double* __restrict__ xout, long long out_stride,
-                const double* __restrict__ S, const GlBatchTables tab, int T, int n_used, int seg_per_cta) {
+                const double* __restrict__ S, const GlBatchTables tab, int T, int n_used, int rpu, int slots_per_cta,
+                long long total_slots) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* s_buf = reinterpret_cast<cplx*>(smem_raw);                        // [kBF][kBufC]
     double* s_carry = reinterpret_cast<double*>(s_buf + kBF * kBufC);       // [kCarry][160]
@@ -111,30 +125,54 @@ k_gl_batch_iter(const double* __restrict__ xin, long long in_stride, double* __r
     for (int i = tid; i < 400; i += kBT) s_twt[i] = tab.tw_half[((i / 20) * (i % 20)) % kM];
     for (int i = tid; i < kM; i += kBT) s_win2[i] = make_double2(tab.window[2 * i], tab.window[2 * i + 1]);
     for (int i = tid; i <= kM / 2; i += kBT) s_twf[i] = tab.tw_full[i];
-    for (int i = tid; i < kCarry * kHopB; i += kBT) s_carry[i] = 0.0;
     __syncthreads();
 
-    const int u = blockIdx.y;
-    const int h0 = blockIdx.x * seg_per_cta, h1 = min(h0 + seg_per_cta, T);
-    const double* xu = xin + (long long)u * in_stride;
-    double* xo = xout + (long long)u * out_stride;
-    const double* Su = S + (long long)u * n_used * kBinsB;
-    const int n_lim = min(n_used, h1);                                      // frames >= h1 only reach segments of the next range
     const int f = tid / 20, l = tid - f * 20;                               // frame of the round, row / column index
     cplx* A = s_buf + f * kBufC;
     constexpr double scale = 1.0 / kN;
+    long long q = (long long)blockIdx.x * slots_per_cta;
+    const long long q_end = min(q + slots_per_cta, total_slots);
+    while (q < q_end) {
+    const int u = (int)(q / rpu), r0 = (int)(q - (long long)u * rpu);
+    const bool to_end = q_end - q >= rpu - r0;                               // the run covers the rest of this utterance
+    const int h0 = r0 ? r0 * kBF + kCarry : 0;
+    const int h1 = to_end ? T : min(T, (r0 + (int)(q_end - q)) * kBF + kCarry);
+    q += to_end ? rpu - r0 : q_end - q;
+    const double* xu = xin + (long long)u * in_stride;
+    double* xo = xout + (long long)u * out_stride;
+    const double* Su = S + (long long)u * n_used * kBinsB;
+    const int n_lim = min(n_used, h1);                                      // frames >= h1 only reach segments of the next run
+#pragma unroll
+    for (int i = 0; i < kCarry; ++i) s_carry[i * kHopB + tid] = 0.0;        // column tid of the carry belongs to thread tid
 
-    for (int g0 = max(h0 - kCarry, 0); g0 < h1; g0 += kBF) {
+    // the raw samples of this thread's frame, requested one round ahead: DRAM latency then overlaps the overlap-add and the
+    // barrier instead of opening pass 1
+    double2 xr[20];
+    if (r0 * kBF + f < n_lim) {
+        const double2* x2 = reinterpret_cast<const double2*>(xu + (long long)(r0 * kBF + f) * kHopB) + l;
+#pragma unroll
+        for (int m = 0; m < 20; ++m) xr[m] = x2[20 * m];
+    }
+    for (int g0 = r0 * kBF; g0 < h1; g0 += kBF) {
         const int n = g0 + f;
         const bool live = n < n_lim;
         cplx v[20];
+        {
+            // the next round's magnitudes come from DRAM (an utterance's 0.9 MB per iteration does not stay in L2 across the 440
+            // utterances in flight): ask for the lines now
+            const int gn = g0 + kBF;
+            if (gn < n_lim) {
+                const char* ps = reinterpret_cast<const char*>(Su + (long long)gn * kBinsB);
+                const int s_bytes = (int)sizeof(double) * kBinsB * min(kBF, n_lim - gn);
+                for (int o = 128 * tid; o < s_bytes; o += 128 * kBT) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + o));
+            }
+        }
         // ---- pass 1: window + pack z[j] = x[2j] w[2j] + i x[2j+1] w[2j+1], j = l + 20 m; transform over m; twiddle ----------
         if (live) {
-            const double2* x2 = reinterpret_cast<const double2*>(xu + (long long)n * kHopB) + l;
 #pragma unroll
             for (int m = 0; m < 20; ++m) {
-                const double2 xv = x2[20 * m], wv = s_win2[l + 20 * m];
-                v[m] = cplx{xv.x * wv.x, xv.y * wv.y};
+                const double2 wv = s_win2[l + 20 * m];
+                v[m] = cplx{xr[m].x * wv.x, xr[m].y * wv.y};
             }
             dft20<-1>(v);
             A[l] = v[pos20(0)];
@@ -150,17 +188,26 @@ k_gl_batch_iter(const double* __restrict__ xin, long long in_stride, double* __r
 #pragma unroll
             for (int k2 = 0; k2 < 20; ++k2) A[l * kRow + k2] = v[pos20(k2)];
         }
+        // the magnitudes of this thread's 10 bin pairs: requested before the barrier, so DRAM latency overlaps the wait
+        double sa[kPairsPerThread], sb[kPairsPerThread];
+#pragma unroll
+        for (int i = 0; i < kPairsPerThread; ++i) {
+            const int p = tid + kBT * i, fp = p / 200, k = 1 + (p - fp * 200), np = g0 + fp;
+            const bool ok = np < n_lim;
+            sa[i] = ok ? Su[(long long)np * kBinsB + k] : 0.0;
+            sb[i] = ok ? Su[(long long)np * kBinsB + kM - k] : 0.0;
+        }
         __syncthreads();
         // ---- bin pairs (k, 400 - k), k = 1..200: split, Z = S X / |X|, inverse split -------------------------------------------
         // with A = Zc[k], B = conj(Zc[400-k]), t = w_k (A - B):  X[k] = E + O, X[400-k] = conj(E - O),  E = (A + B)/2, O = -i t/2
         // and back:  Zin[k] = s + r, Zin[400-k] = conj(s - r),  s = Z[k] + conj(Z[400-k]),  r = i conj(w_k) (Z[k] - conj(Z[400-k]))
-#pragma unroll 2
-        for (int p = tid; p < kBF * 200; p += kBT) {
-            const int fp = p / 200, k = 1 + (p - fp * 200), k2 = kM - k, np = g0 + fp;
-            if (np >= n_lim) continue;
+#pragma unroll
+        for (int i = 0; i < kPairsPerThread; ++i) {
+            const int p = tid + kBT * i, fp = p / 200, k = 1 + (p - fp * 200), k2 = kM - k;
+            if (g0 + fp >= n_lim) continue;
             cplx* Ap = s_buf + fp * kBufC;
             const int ia = (k % 20) * kRow + k / 20, ib = (k2 % 20) * kRow + k2 / 20;
-            const double sk = Su[(long long)np * kBinsB + k], sk2 = Su[(long long)np * kBinsB + k2];
+            const double sk = sa[i], sk2 = sb[i];
             const cplx Za = Ap[ia], Zb = Ap[ib], w = s_twf[k];
             const cplx d = cplx{Za.x - Zb.x, Za.y + Zb.y}, t = cmul(w, d);
             const double ex = 0.5 * (Za.x + Zb.x), ey = 0.5 * (Za.y - Zb.y);
@@ -208,6 +255,17 @@ k_gl_batch_iter(const double* __restrict__ xin, long long in_stride, double* __r
                 A[m * kRow + l] = cplx{(v[pos20(m)].x * scale) * wv.x, (v[pos20(m)].y * scale) * wv.y};
             }
         }
+        {
+            // (assigned on every path, so that the registers are free between pass 1 and here)
+            const bool more = n + kBF < n_lim;
+            const double2* x2 = reinterpret_cast<const double2*>(xu + (long long)(more ? n + kBF : 0) * kHopB) + l;
+#pragma unroll
+            for (int m = 0; m < 20; ++m) xr[m] = make_double2(0.0, 0.0);
+            if (more) {
+#pragma unroll
+                for (int m = 0; m < 20; ++m) xr[m] = x2[20 * m];
+            }
+        }
         __syncthreads();
         // ---- overlap-add: segments g0 .. g0+kBF-1 are final, the next 4 stay open ---------------------------------------------------
         {
@@ -230,6 +288,7 @@ k_gl_batch_iter(const double* __restrict__ xin, long long in_stride, double* __r
             }
         }
         __syncthreads();
+    }
     }
 }
 
@@ -266,23 +325,14 @@ int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int 
         const size_t smem = sizeof(cplx) * (kBF * kBufC + 400 + kM / 2 + 1) + sizeof(double) * kCarry * kHopB + sizeof(double2) * kM;
         static unsigned long long optin = 0;
         SGS_CUDA(smem_optin(k_gl_batch_iter, smem, &optin));
-        // hop segments per CTA: whole utterances when there are enough of them to fill the device several times over, else
-        // ranges (each range re-computes the 4 frames before it, so no sum crosses a CTA)
         int dev = 0, sms = 148;
         SGS_CUDA(cudaGetDevice(&dev));
         SGS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const long long slots = 3LL * sms;
-        int parts = 1, seg = T;
-        long long best = -1;
-        for (int want = 1; want <= 8; want *= 2) {
-            int sg = (T + want - 1) / want;
-            sg = (sg + 3) / kBF * kBF + kBF - kCarry;                        // segments + the 4 re-computed frames = whole rounds
-            if (want > 1 && sg < 3 * kBF) break;
-            const int np = (T + sg - 1) / sg;
-            const int rounds = np == 1 ? (T + kBF - 1) / kBF : (sg + kCarry + kBF - 1) / kBF;
-            const long long cost = (((long long)n_utt * np + slots - 1) / slots) * rounds;
-            if (best < 0 || cost < best) { best = cost; parts = np; seg = sg; }
-        }
+        const int rpu = (T + kBF - 1) / kBF;                                 // rounds per utterance
+        const long long slots = 3LL * sms, total = (long long)n_utt * rpu;   // CTAs resident at once; rounds in all
+        int per_cta = rpu;                                                   // whole utterances ...
+        if (n_utt < 4 * slots) per_cta = (int)std::max<long long>((total + slots - 1) / slots, std::min(rpu, 2));   // ... or equal runs
+        const int grid = (int)((total + per_cta - 1) / per_cta);
         double *y = nullptr, *S = nullptr;
         SGS_CUDA(cudaMallocAsync((void**)&y, sizeof(double) * (size_t)n_utt * n, st));
         SGS_CUDA(cudaMallocAsync((void**)&S, sizeof(double) * (size_t)n_utt * n_used * kBinsB, st));
@@ -292,8 +342,8 @@ int gl_batch_run(const double* logmel, double* x, const GlBatchTables& tab, int 
             ProfScope ps(kProfGlBatch, st);
             for (int it = 0; it < iters; ++it) {
                 const bool fwd = (it & 1) == 0;                              // x -> y on even iterations, y -> x on odd ones
-                k_gl_batch_iter<<<dim3(parts, n_utt), kBT, smem, st>>>(fwd ? x : y, fwd ? x_len : n, fwd ? y : x, fwd ? n : x_len, S, tab,
-                                                                       T, n_used, seg);
+                k_gl_batch_iter<<<grid, kBT, smem, st>>>(fwd ? x : y, fwd ? x_len : n, fwd ? y : x, fwd ? n : x_len, S, tab, T, n_used,
+                                                         rpu, per_cta, total);
                 SGS_LAUNCHED();
             }
         }
