@@ -2,13 +2,16 @@
 multiprocessing.Manager list so that frames appended in a forked feeder process are visible to the parent.
 
 The reference pays one Manager round trip (pickle + socket + unpickle, ~0.1 ms) per frame and receiver, on the
-thread that runs the whole graph.  Here frames are kept in a process-local list and moved to the Manager list in
-batches: every `flush_interval` seconds of streaming, when the process exits (a multiprocessing finalizer, so it
-also runs in a forked feeder), and whenever `get_data` / `stop_processing` run in the collecting process.
-The periodic hand-over runs on a flusher thread of the collecting process, not on the graph thread: a batch of
-0.25 s of 128-channel sEEG is a 0.3-0.7 ms Manager round trip, which on the graph thread was the p99 of the frame
-latency when packets arrive in real time (one packet in eight paid it).  `flush_interval=0` restores the per-frame
-behaviour."""
+thread that runs the whole graph.  Here frames are kept in a process-local list and moved to the Manager list when
+`get_data` / `stop_processing` / `flush` run in the collecting process, when that process exits (a multiprocessing
+finalizer, so it also runs in a forked feeder) or is terminated (SIGTERM hook below), and when more than
+`max_held_bytes` have piled up.  Nothing is handed over while frames stream, by default: measured on the 128-channel
+chain (tools/latency_tail.py, 30 s legs), every frame slower than 1 ms - 9 of 2990 with packets arriving in real time,
+a 45 ms stall when a recording is replayed back to back - came from a hand-over, also when it ran on a flusher thread
+in small batches (the thread pickles under the interpreter lock the graph thread needs); without hand-overs the slowest
+frame took 0.50 ms back to back and 0.72 ms in real time.  A process that polls `get_data` on a Receiver fed by ANOTHER
+process therefore sees the frames only after the feeder has flushed; `flush_interval=<seconds>` restores a timed
+hand-over (on a flusher thread, at most `max_batch` frames at a time), `flush_interval=0` the reference's per-frame one."""
 import multiprocessing
 import multiprocessing.util
 import os
@@ -55,12 +58,17 @@ def _register(receiver):
 
 
 class Receiver(Node.Node):
-    def __init__(self, perform_timing=False, dont_time=False, name='Receiver', flush_interval=0.25):
+    def __init__(self, perform_timing=False, dont_time=False, name='Receiver', flush_interval=None, max_batch=32,
+                 max_held_bytes=2 << 30):
         super().__init__(has_outputs=False, dont_time=dont_time, name=name)
         self._manager = multiprocessing.Manager()
         self.data = self._manager.list([])
         self.perform_timing = perform_timing
-        self.flush_interval = flush_interval
+        env = os.environ.get('SGS_RECEIVER_FLUSH_INTERVAL')
+        self.flush_interval = (None if env in ('', 'none', 'None') else float(env)) if env is not None else flush_interval
+        self.max_batch = int(os.environ.get('SGS_RECEIVER_MAX_BATCH', max_batch))
+        self.max_held_bytes = max_held_bytes
+        self._held_bytes = 0
         self._local = []
         self._local_pid = None
         self._last_flush = 0.0
@@ -99,7 +107,12 @@ class Receiver(Node.Node):
             self._adopt_process()
         now = time.time()
         self._local.append([now, sample] if self.perform_timing else sample)
-        if now - self._last_flush >= self.flush_interval:
+        self._held_bytes += getattr(sample, 'nbytes', 64)
+        if self.flush_interval is None:
+            if self._held_bytes > self.max_held_bytes:
+                self.flush()
+            return
+        if now - self._last_flush >= self.flush_interval or (self.max_batch > 0 and len(self._local) >= self.max_batch):
             if self.flush_interval <= 0:
                 self.flush()
                 return
@@ -110,6 +123,7 @@ class Receiver(Node.Node):
                                                 name=self.name + '-flusher')
                 self._thread.start()
             batch, self._local = self._local, []
+            self._held_bytes = 0
             self._queue.put(batch)
             self._last_flush = now
 
@@ -122,6 +136,7 @@ class Receiver(Node.Node):
             if self._local:
                 pending.append(self._local)
                 self._local = []
+            self._held_bytes = 0
             for batch in pending:
                 self.data.extend(batch)
         self._last_flush = time.time()

@@ -257,6 +257,21 @@ def test_exp_angle_tables_match_generator():
     assert worst < 1.5 * 2.2e-16
 
 
+def test_receiver_holds_frames_until_asked_by_default():
+    """No Manager round trip while frames stream (every frame over 1 ms of the latency leg was one, tools/latency_tail.py):
+    the default Receiver hands over in get_data / stop_processing / flush, or once max_held_bytes have piled up."""
+    from livenodes import Receiver
+    rec = Receiver.Receiver()
+    for i in range(10):
+        rec.add_data(np.full(4, i))
+    assert rec._thread is None and len(rec.data) == 0
+    assert [int(a[0]) for a in rec.get_data()] == list(range(10))
+    small = Receiver.Receiver(max_held_bytes=100)
+    for i in range(5):
+        small.add_data(np.zeros(8))                      # 64 bytes each: the second frame crosses the limit
+    assert len(small.data) == 4 and len(small.get_data()) == 5
+
+
 def test_receiver_timed_flush_runs_off_the_graph_thread():
     """Timed hand-overs go through the flusher thread; order is kept and a synchronous flush drains the queue first."""
     import threading
