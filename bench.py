@@ -456,7 +456,7 @@ def run_ours(args):
                 {"kernel": "k_gl_blocks8 (Griffin-Lim node blocks)", "bound": "fp64 pipe (HBM traffic is 80 doubles in, 480 out per block)",
                  "achieved": (S * (n_frames - 1) * 164e3 / (prof['gl_blocks'][0] / args.steps * 1e-3)) if prof['gl_blocks'][0] > 0 else None,
                  "peak": 2 * FP64_PEAK, "unit": "fp64 flop/s (164 kflop nominal per 10 ms frame, SURVEY.md 8d)",
-                 "note": "pipe busy 54 % by ncu (profiles/ncu_gl_blocks8_r01b.txt), bound by dependent latency at 4 warps per scheduler; the nominal 5 N log2 N count leaves out exp(angle) and the splits"},
+                 "note": "pipe busy 57 % by ncu (profiles/ncu_gl_blocks8_r02.txt): 1202 of 2503 instructions per warp-iteration are fp64, 16 warps per SM at 128 registers, 6.6 cycles between a warp's instructions; the nominal 5 N log2 N count leaves out exp(angle) and the splits"},
                 {"kernel": "k_lda_tc (LDA scoring, tcgen05 kind::tf32)", "bound": "tensor", "ms_per_launch": lda_tc_ms,
                  "achieved": (2.0 * S * n_frames * 150 * 360 / 1e12 / (lda_tc_ms * 1e-3)) if lda_tc_ms > 0 else None,
                  "issued": (2.0 * S * n_frames * 160 * 384 * 3 / 1e12 / (lda_tc_ms * 1e-3)) if lda_tc_ms > 0 else None,
@@ -473,6 +473,7 @@ def run_ours(args):
             "clocks": sampler.summary() if sampler is not None else None,
         }
         line["cpu_baseline"] = cpu_baseline_sample(decoder) if world == 1 else None      # rank 0 at N = 1 only (the other ranks would wait for it)
+        line["cpu_baseline_as_shipped"] = as_shipped_reference() if world == 1 else None
         line["latency"] = latency_leg() if world == 1 and not args.no_latency else None
         line["config4"], line["config3"] = c4, c3
         print(json.dumps(line), flush=True)
@@ -506,6 +507,31 @@ def _cpu_decode_one(args, full=False):
     if full:
         return x, feats, labels, spec, noise, pcm
     return len(pcm)
+
+
+def as_shipped_reference(timeout_s=240):
+    """The UNMODIFIED reference timed on this host (one core, as it runs): its livenodes chain, its function-level batch path
+    and train.train on bounded samples of the 128-channel workload (oracle/time_reference.py, a subprocess so that the
+    reference's `livenodes` / `local` packages and the product's never meet).  Needs the copy of the reference tree that
+    __graft_entry__.build() stages under the git-ignored baseline/_ref/ in the build container."""
+    import subprocess
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'livenodes')):
+        return {"unavailable": "no reference tree under baseline/_ref (staged by __graft_entry__.build() where /root/reference exists)"}
+    env = dict(os.environ, SGS_REFERENCE_ROOT=ref, OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1')
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'time_reference.py'), '4', '20', '30'], env=env,
+                           capture_output=True, text=True, timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+        if not lines:
+            return {"unavailable": "oracle/time_reference.py printed no result", "stderr_tail": r.stderr[-300:]}
+        out = json.loads(lines[-1])
+        out["kind"] = "reference"
+        out["unit"] = UNIT
+        out["value"] = out["as_shipped_chain"]["channel_seconds_per_s"]
+        return out
+    except Exception as e:                                     # a baseline that cannot be timed must not take the bench line with it
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
 
 def cpu_baseline_sample(decoder, seconds=20.0):
@@ -548,11 +574,13 @@ def run_reference(args):
         dt = (time.perf_counter() - t0) / args.steps
     value = cores * N_CH * seconds / dt
     sample = "oracle port (numpy/scipy closed form of the reference node chain), %d processes x 1 session x %d ch x %g s @ %d Hz per step" % (cores, N_CH, seconds, SR)
+    shipped = as_shipped_reference()       # the unmodified reference on one core, as it runs (not the line's value: the port on all cores is the stronger baseline)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get('WORLD_SIZE', '1')), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline_as_shipped": shipped,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
