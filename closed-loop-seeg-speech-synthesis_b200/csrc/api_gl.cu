@@ -399,6 +399,12 @@ int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* 
 
 extern "C" {
 
+int sgs_gl_node_rebase(sgs_gl_node* s, int32_t delta) {
+    SGS_ARG(s, "NULL argument");
+    for (int i = 0; i < sgs::kBlockRing; ++i) s->ring_pos[i] -= delta;
+    return SGS_OK;
+}
+
 /* Streaming form: feed `n` new spectral frames (host), get the audio the node would have emitted for them. */
 int sgs_gl_node_push(sgs_gl_node* s, const double* logmel, int n, const int32_t* pos, int32_t pos_before, const double* noise,
                      uint64_t seed, int16_t* pcm, int* n_pcm, void* stream) {

@@ -41,18 +41,32 @@ class GriffinLimSynthesis(Node.Node):
         self.device_noise = device_noise
         self._pcm = np.empty(16 * 192, dtype=np.int16)
         self._chain = None              # set by sgs.chain.FusedChain
+        self._pos_base = 0
+
+    _REBASE_AT = 1 << 30
+
+    def _head(self):
+        """Write head before the next frame, in the 32-bit coordinates the library is given: the absolute sample count (the
+        reference's float expression, quirk Q7) minus a base that moves up before the count outgrows an int32 - the library
+        only uses differences of positions (the reference keeps them modulo its ring length and so runs for ever too)."""
+        prev = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)
+        if prev - self._pos_base >= self._REBASE_AT:
+            delta = prev - self._pos_base
+            _lib.check(_lib.lib().sgs_gl_node_rebase(self._op.handle(), delta))
+            self._pos_base += delta
+        return prev - self._pos_base
 
     def _reserve(self, n):
         """Host bookkeeping of add_data for the next n frames at once (fused chain): write-head positions, the
         np.random.rand(480) draws in frame order, and which frames emit audio."""
-        prev = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)
+        prev = self._head()
         pos = np.empty(n, dtype=np.int32)
         emit = [False] * n
         noise = None if self.device_noise else np.zeros((n, self.blockLen * self.frameShift))
         for i in range(n):
             self.framePos += 1
             self.outputBufferPosMs += self.frameShiftMs
-            pos[i] = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)
+            pos[i] = int((self.outputBufferPosMs / 1000.0) * self.sampleRate) - self._pos_base
             emit[i] = not (self.framePos < self.blockLen - self.contextWidth)
             if emit[i] and noise is not None:
                 noise[i] = np.random.rand(self.blockLen * self.frameShift)
@@ -69,9 +83,9 @@ class GriffinLimSynthesis(Node.Node):
             return
         frame = np.ascontiguousarray(np.asarray(dataFrame, dtype=np.float64).reshape(1, -1))
         self.framePos += 1
-        prev = int((self.outputBufferPosMs / 1000.0) * self.sampleRate)
+        prev = self._head()
         self.outputBufferPosMs += self.frameShiftMs
-        pos = np.array([int((self.outputBufferPosMs / 1000.0) * self.sampleRate)], dtype=np.int32)
+        pos = np.array([int((self.outputBufferPosMs / 1000.0) * self.sampleRate) - self._pos_base], dtype=np.int32)
         first = self.framePos < self.blockLen - self.contextWidth
         noise = None
         if not first and not self.device_noise:

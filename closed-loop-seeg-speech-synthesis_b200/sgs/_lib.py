@@ -58,6 +58,7 @@ def _declare(lib):
     fn('sgs_sos_stream_create', c_int, C.POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int)
     fn('sgs_sos_stream_destroy', None, c_void_p)
     fn('sgs_sos_stream_push', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p)
+    fn('sgs_gl_node_rebase', c_int, c_void_p, C.c_int32)
     fn('sgs_gl_node_push', c_int, c_void_p, c_void_p, c_int, c_void_p, C.c_int32, c_void_p, C.c_uint64, c_void_p,
        C.POINTER(c_int), c_void_p)
     fn('sgs_chain_create', c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_void_p)

@@ -169,6 +169,12 @@ int sgs_gl_node_synthesize(sgs_gl_node* node, const double* logmel, int n_sessio
 int sgs_gl_node_push(sgs_gl_node* node, const double* logmel, int n, const int32_t* pos, int32_t pos_before,
                      const double* noise, uint64_t seed, int16_t* pcm, int* n_pcm, void* stream);
 
+/* Write-head positions are absolute sample counts in 32 bits (37 h of audio at 16 kHz); only their differences matter.
+ * Subtracts `delta` from every position the node remembers, so that a long-running caller can keep passing small numbers
+ * (the reference keeps its positions modulo the ring length, GriffinLim.py:115-166, and so runs indefinitely): after the
+ * call, pos / pos_before of sgs_gl_node_push and sgs_chain_push are expected in the shifted coordinates. */
+int sgs_gl_node_rebase(sgs_gl_node* node, int32_t delta);
+
 /* ---------------------------------------------------------------------------------------------------
  * Fused streaming chain: the four nodes decode.py:152-183 wires (ECogFeatCalc -> LDASynthesis -> Dequantization ->
  * GriffinLimSynthesis), driven back to back on one CUDA stream with ONE host<->device round trip per packet of

@@ -183,6 +183,17 @@ def test_fused_chain_equals_node_by_node(model, packet, chunk_size):
     assert {len(p) for p in a[3]} <= {159, 160, 161}
 
 
+@pytest.mark.parametrize('fused', [True, False])
+def test_write_head_rebase_changes_nothing(model, fused, monkeypatch):
+    """Write-head positions travel as int32 sample counts (37 h at 16 kHz); the node shifts them down before they outgrow that
+    (sgs_gl_node_rebase) - here every 2000 samples, 15 times in 2 s - and emits the same hops as without."""
+    from livenodes import GriffinLim
+    want = _run_graph(model, fused, 64, chunk_size=64)
+    monkeypatch.setattr(GriffinLim.GriffinLimSynthesis, '_REBASE_AT', 2000)
+    got = _run_graph(model, fused, 64, chunk_size=64)
+    assert len(got[3]) == len(want[3]) > 150 and all(np.array_equal(p, q) for p, q in zip(got[3], want[3]))
+
+
 def test_fused_chain_not_used_for_other_wirings(model):
     """A second consumer between the nodes, or a missing node, keeps the per-node path."""
     from livenodes import Node, ECogFeatCalc, LDASynthesis, Dequantization, LambdaNode
