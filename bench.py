@@ -240,7 +240,9 @@ def config3_leg(world, rank, dist, barrier):
            "wall_s": wall, "rows": int(x_train.shape[0]), "channel_seconds_per_s": N_CH * C3_SECONDS / wall,
            "stage_s_rank0": {k: round(v, 4) for k, v in prof.items() if k.endswith('_s')},
            "h2d_bytes_rank0": prof.get('h2d_bytes'),
-           "collectives_rank0": {"rho_allgather_bytes": prof.get('rho_allgather_bytes'), "columns_allreduce_bytes": prof.get('columns_allreduce_bytes'),
+           "collectives_rank0": {"audio_allreduce_bytes": prof.get('audio_allreduce_bytes'),
+                                 "audio_allreduce_us": round(1e6 * prof.get('audio_allreduce_s', 0.0), 1),
+                                 "rho_allgather_bytes": prof.get('rho_allgather_bytes'), "columns_allreduce_bytes": prof.get('columns_allreduce_bytes'),
                                  "columns_allreduce_us": round(1e6 * prof.get('columns_allreduce_s', 0.0), 1),
                                  "stats_allreduce_bytes": prof.get('stats_allreduce_bytes'),
                                  "stats_allreduce_us": round(1e6 * prof.get('stats_allreduce_s', 0.0), 1)},

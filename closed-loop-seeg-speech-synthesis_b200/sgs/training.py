@@ -284,8 +284,21 @@ def sharded_fit(eeg, audio, sfreq_eeg, sfreq_audio, nb_mel_bins=40, nb_intervals
     c0, c1 = block_shard(C, rank, world)
     t0 = time.perf_counter()
     eeg_d = ops.upload(eeg[:, c0:c1])
-    audio_d = ops.upload(audio, np.float64)
-    prof['h2d_bytes'] = 0 if _lib._is_torch(eeg) else int(eeg[:, c0:c1].nbytes + np.asarray(audio).size * 8)
+    if world > 1 and not _lib._is_torch(audio):
+        # every rank needs the whole audio (the target spectrogram is computed replicated), but not over its own PCIe link and
+        # out of the one host memory all ranks share: each uploads 1/world of it and the pieces are summed into place over NVLink
+        a_lo, a_hi = block_shard(len(audio), rank, world)
+        audio_d = ops.zeros((len(audio),), like=eeg_d)
+        if a_hi > a_lo:
+            audio_d[a_lo:a_hi] = ops.upload(np.asarray(audio)[a_lo:a_hi], np.float64)
+        prof['h2d_bytes'] = int(eeg[:, c0:c1].nbytes + (a_hi - a_lo) * 8)
+        lap('h2d_s', t0)
+        prof['audio_allreduce_bytes'], prof['audio_allreduce_s'] = _allreduce_sum_(audio_d, group)
+        t0 = time.perf_counter()
+    else:
+        audio_d = ops.upload(audio, np.float64)
+        prof['h2d_bytes'] = 0 if _lib._is_torch(eeg) else int(eeg[:, c0:c1].nbytes + np.asarray(audio).size * 8)
+        prof['audio_allreduce_bytes'], prof['audio_allreduce_s'] = 0, 0.0
     lap('h2d_s', t0)
 
     t0 = time.perf_counter()
