@@ -270,6 +270,7 @@ struct sgs_feat_stream {
     sgs_feat_plan* plan = nullptr;
     int n_channels = 0, frame_size = 0, order = 0, step = 0;
     long long consumed = 0;
+    bool cold = false;                  // ECogFeatCalc(warm_start=False): the last filter starts cold, no zero fill in front
     double *d_z = nullptr, *d_sq = nullptr, *d_feat = nullptr, *d_out = nullptr;
     void* d_x = nullptr;
     size_t x_cap = 0;
@@ -302,8 +303,8 @@ int feat_stream_enqueue(sgs_feat_stream* s, const void* x, int x_is_f64, int n, 
     int rc = copy_in_small(s->d_x, x, bytes, src_pinned, st);
     if (rc != SGS_OK) return rc;
     rc = feat_stream_run(s->plan->n_biquads, s->d_x, x_is_f64 != 0, n, s->n_channels, s->consumed, s->d_z, s->d_sq, s->d_feat,
-                             s->plan->d_zf, s->plan->zero_fill, s->frame_size, s->order, s->step, d_rows ? d_rows : s->d_out,
-                             s->plan->cf, fr, st);
+                             s->plan->d_zf, s->cold ? 0 : s->plan->zero_fill, s->cold ? 1 : 0, s->frame_size, s->order, s->step,
+                             d_rows ? d_rows : s->d_out, s->plan->cf, fr, st);
     if (rc != SGS_OK) return rc;
     s->consumed += n;
     return SGS_OK;
@@ -316,6 +317,13 @@ void sgs_feat_stream_destroy(sgs_feat_stream* s) {
     if (!s) return;
     cudaFree(s->d_z); cudaFree(s->d_sq); cudaFree(s->d_feat); cudaFree(s->d_out); cudaFree(s->d_x);
     delete s;
+}
+
+int sgs_feat_stream_set_cold_start(sgs_feat_stream* s, int cold) {
+    SGS_ARG(s, "NULL argument");
+    SGS_ARG(s->consumed == 0, "the start mode can only be chosen before the first push");
+    s->cold = cold != 0;
+    return SGS_OK;
 }
 
 int sgs_feat_stream_create(sgs_feat_stream** stream_out, sgs_feat_plan* plan, int n_channels, int frame_size, int order, int step) {

@@ -27,7 +27,7 @@ struct sgs_gl_batch {
 };
 
 struct sgs_gl_node {
-    int n_mels = 0, iterations = 0, first_frame = 1;
+    int n_mels = 0, iterations = 0, first_frame = 1, log_mels = 1;
     double norm_div = 1.01;
     sgs::LpCoefs lp;
     double *d_window = nullptr, *d_ola = nullptr, *d_inv_w = nullptr, *d_phi = nullptr, *d_phi_sub = nullptr;
@@ -220,7 +220,7 @@ int sgs_gl_node_synthesize(sgs_gl_node* n, const double* logmel, int n_sessions,
         if (e != cudaSuccess) rc = cuda_fail(e, "scratch", __FILE__, __LINE__);
     }
     if (rc == SGS_OK) {
-        GlNodeTables tab{n->d_window, n->d_tw_full, n->d_tw_t, n->d_inv_idx, n->d_inv_w};
+        GlNodeTables tab{n->d_window, n->d_tw_full, n->d_tw_t, n->d_inv_idx, n->d_inv_w, n->log_mels};
         rc = gl_blocks_run((const double*)s_mel.dev, (const double*)s_noise.dev, seed, d_blocks, tab, n_sessions, n_frames,
                            n->n_mels, first, n->iterations, 0, 0, st);
     }
@@ -382,7 +382,7 @@ int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* 
     for (int i = 0; i < kBlockRing; ++i) { fr.ring_pos[i] = s->ring_pos[i]; fr.ring_index[i] = s->ring_index[i]; }
     int rc = SGS_OK;
     if (fr.n > 0) {
-        GlNodeTables tab{s->d_window, s->d_tw_full, s->d_tw_t, s->d_inv_idx, s->d_inv_w};
+        GlNodeTables tab{s->d_window, s->d_tw_full, s->d_tw_t, s->d_inv_idx, s->d_inv_w, s->log_mels};
         // local frame j (row j of d_mel) is running frame k0 - 1 + j; blocks for local frames [1 + skip, n]
         rc = gl_blocks_run(s->d_mel, noise ? s->d_noise : nullptr, seed, s->d_ring, tab, 1, n + 1, nm, 1 + skip, s->iterations,
                            k0 - 1, kBlockRing, st);
@@ -398,6 +398,12 @@ int gl_node_enqueue(sgs_gl_node* s, const double* logmel, int n, const int32_t* 
 }  // namespace sgs
 
 extern "C" {
+
+int sgs_gl_node_set_log_mels(sgs_gl_node* s, int log_mels) {
+    SGS_ARG(s, "NULL argument");
+    s->log_mels = log_mels ? 1 : 0;
+    return SGS_OK;
+}
 
 int sgs_gl_node_rebase(sgs_gl_node* s, int32_t delta) {
     SGS_ARG(s, "NULL argument");

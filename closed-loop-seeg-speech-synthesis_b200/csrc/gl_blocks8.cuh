@@ -89,6 +89,7 @@ struct G8Tables {
     const cplx* tw_full;       // exp(-2 pi i k / 256), k <= 128
     const int* inv_idx;
     const double* inv_w;
+    int log_mels;              // fromLogMels (exp, non-finite -> 0) or fromMels (as given)
 };
 
 // magnitudes are stored as partner pairs (S[p], S[128 - p]) at index p <= 64, so the phase step fetches both with one load
@@ -174,7 +175,7 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
             const double* lm = logmel + (frame - 1 + frm) * n_mels;
             if (n_mels <= kG8MelMax) {
 #pragma unroll 1
-                for (int m = l8; m < n_mels; m += 8) em[m] = exp(lm[m]);
+                for (int m = l8; m < n_mels; m += 8) em[m] = tab.log_mels ? exp(lm[m]) : lm[m];
                 __syncwarp();
 #pragma unroll 2
                 for (int b = l8; b < kBins; b += 8) {
@@ -183,11 +184,11 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                     const double e0 = em[id.x], e1 = em[id.y];
                     double v = (w.x != 0.0) ? e0 * w.x : 0.0;
                     v = (w.y != 0.0) ? fma(e1, w.y, v) : v;
-                    v = isfinite(v) ? v : 0.0;                              // MelFilterBank.makeNormal
+                    v = (tab.log_mels && !isfinite(v)) ? 0.0 : v;           // MelFilterBank.makeNormal (fromLogMels only)
                     g8_store_mag(Sw, b, v);
                 }
             } else {
-                for (int b = l8; b < kBins; b += 8) g8_store_mag(Sw, b, mel_magnitude(lm, tab.inv_idx, tab.inv_w, b));
+                for (int b = l8; b < kBins; b += 8) g8_store_mag(Sw, b, mel_magnitude(lm, tab.inv_idx, tab.inv_w, b, tab.log_mels));
             }
         }
         // the initial waveform: into the (still unused) transposition space, then into the register slots

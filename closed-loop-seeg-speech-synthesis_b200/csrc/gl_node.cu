@@ -36,12 +36,12 @@ __device__ __forceinline__ double uniform01(unsigned long long seed, unsigned lo
 }
 
 // fromLogMels for one bin through the 2-tap inverse mel matrix (MelFilterBank.py:82-83), out of line (once per block)
-__device__ __noinline__ double mel_magnitude(const double* lm, const int* inv_idx, const double* inv_w, int bin) {
+__device__ __noinline__ double mel_magnitude(const double* lm, const int* inv_idx, const double* inv_w, int bin, int log_mels) {
     const double w0 = inv_w[bin * 2], w1 = inv_w[bin * 2 + 1];
     double v = 0.0;
-    if (w0 != 0.0) v = exp(lm[inv_idx[bin * 2]]) * w0;
-    if (w1 != 0.0) v = fma(exp(lm[inv_idx[bin * 2 + 1]]), w1, v);
-    return isfinite(v) ? v : 0.0;                                           // MelFilterBank.makeNormal
+    if (w0 != 0.0) v = (log_mels ? exp(lm[inv_idx[bin * 2]]) : lm[inv_idx[bin * 2]]) * w0;
+    if (w1 != 0.0) v = fma(log_mels ? exp(lm[inv_idx[bin * 2 + 1]]) : lm[inv_idx[bin * 2 + 1]], w1, v);
+    return (log_mels && !isfinite(v)) ? 0.0 : v;                            // MelFilterBank.makeNormal (fromLogMels only)
 }
 
 // out-of-line copy of the four-wide evaluation: one body in the instruction cache, called 4 times per iteration (inlined
@@ -319,7 +319,7 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
                         sizeof(double) * kEaTabLen + sizeof(G8WarpSmem) * W;
     const long long n_pairs = (n_items + 1) / 2, want = (n_pairs + W - 1) / W;
     const int grid = (int)(want < 148LL * 4 ? want : 148LL * 4);
-    const G8Tables t8{tab.window, tab.tw_t, tab.tw_full, tab.inv_idx, tab.inv_w};
+    const G8Tables t8{tab.window, tab.tw_t, tab.tw_full, tab.inv_idx, tab.inv_w, tab.log_mels};
     static unsigned long long optin = 0;
     SGS_CUDA(smem_optin(k_gl_blocks8<W, 1>, smem, &optin));
     k_gl_blocks8<W, 1><<<grid, W * 32, smem, st>>>(logmel, noise, seed, blocks, t8, n_frames, n_mels, first_frame, iters, n_items,

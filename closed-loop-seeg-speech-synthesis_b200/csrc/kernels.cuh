@@ -30,8 +30,8 @@ struct StreamFrames {                   // frames completed by one streaming pus
     long long index[kMaxFramesPerPush]; // running frame number k
 };
 int feat_stream_run(int n_biquads, const void* x, bool x_is_f64, int n, int n_channels, long long t0, double* z,
-                    double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int frame_size, int order, int step,
-                    double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st);
+                    double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int cold_last, int frame_size, int order,
+                    int step, double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st);
 
 constexpr int kSosMaxSections = 8;
 struct SosCoefs { double c[kSosMaxSections][5]; double zi[kSosMaxSections][2]; int n_sections; };   // b0 b1 b2 a1 a2; sosfilt_zi
@@ -71,6 +71,7 @@ struct GlNodeTables {                   // device pointers, built once per node 
     const cplx* tw_t;                   // [2][16][9] W128^((l + 48 f) k1) (register-FFT kernel, gl_blocks8.cuh)
     const int* inv_idx;                 // [129][2] mel index of each inverse-mel tap
     const double* inv_w;                // [129][2] weight (0 where unused)
+    int log_mels;                       // 1: input frames are log-mels (fromLogMels), 0: linear mels (fromMels, GriffinLim.py:84-87)
 };
 struct LpCoefs { double b[kLpMaxOrd + 1], a[kLpMaxOrd + 1]; int ord; };
 struct EmitFrames {                     // streaming emission schedule of one push

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128)
 k_feat_stream(const TIn* __restrict__ x, int n, int n_channels, long long t0 /*samples consumed before this call*/,
               double* __restrict__ z /*[2*NB][C]*/, double* __restrict__ sq_ring /*[kSqRing][C]*/,
               double* __restrict__ feat_ring /*[kFeatRing][C]*/, const double* __restrict__ zero_fill_resp, int zero_fill,
-              int frame_size, int order, int step, double* __restrict__ out /*[frames][C*(order+1)]*/,
+              int cold_last, int frame_size, int order, int step, double* __restrict__ out /*[frames][C*(order+1)]*/,
               const __grid_constant__ FeatCoefs cf, const __grid_constant__ StreamFrames fr) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_channels) return;
@@ -30,15 +30,16 @@ k_feat_stream(const TIn* __restrict__ x, int n, int n_channels, long long t0 /*s
     int first = 0;
     if (t0 == 0) {
         // cold start on the very first sample (FrameBuffer.py:87-98): filter f starts from zi * (its first input),
-        // the last one from its warm-started state
+        // the last one from its warm-started state - or cold like the others (ECogFeatCalc(warm_start=False))
         double v = (double)x[c];
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
 #pragma unroll
             for (int s = 0; s < kSecPerFilter; ++s) {
                 const int i = f * kSecPerFilter + s;
-                z0[i] = (f == NF - 1) ? cf.zi_warm[s][0] : cf.zi[i][0] * v;
-                z1[i] = (f == NF - 1) ? cf.zi_warm[s][1] : cf.zi[i][1] * v;
+                const bool warm = f == NF - 1 && !cold_last;
+                z0[i] = warm ? cf.zi_warm[s][0] : cf.zi[i][0] * v;
+                z1[i] = warm ? cf.zi_warm[s][1] : cf.zi[i][1] * v;
             }
 #pragma unroll
             for (int s = 0; s < kSecPerFilter; ++s) {
@@ -94,12 +95,12 @@ k_feat_stream(const TIn* __restrict__ x, int n, int n_channels, long long t0 /*s
 }
 
 int feat_stream_run(int n_biquads, const void* x, bool x_is_f64, int n, int n_channels, long long t0, double* z,
-                    double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int frame_size, int order, int step,
-                    double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st) {
+                    double* sq_ring, double* feat_ring, const double* zf, int zero_fill, int cold_last, int frame_size, int order,
+                    int step, double* out, const FeatCoefs& cf, const StreamFrames& fr, cudaStream_t st) {
     const int grid = ceil_div(n_channels, 128);
     ProfScope ps(kProfStream, st);
 #define SGS_LAUNCH(NB, T) k_feat_stream<NB, T><<<grid, 128, 0, st>>>((const T*)x, n, n_channels, t0, z, sq_ring, feat_ring, zf, \
-                                                                     zero_fill, frame_size, order, step, out, cf, fr)
+                                                                     zero_fill, cold_last, frame_size, order, step, out, cf, fr)
     if (n_biquads == 24) { if (x_is_f64) SGS_LAUNCH(24, double); else SGS_LAUNCH(24, float); }
     else if (n_biquads == 16) { if (x_is_f64) SGS_LAUNCH(16, double); else SGS_LAUNCH(16, float); }
     else { set_error("unsupported biquad count %d", n_biquads); return SGS_ERR_UNSUPPORTED; }

@@ -23,8 +23,9 @@ class ECogFeatCalc(Node.Node):
     def __init__(self, sample_rate, frame_len_ms, frame_shift_ms, model_order=4, step_size=5,
                  line_noise=50, warm_start=True, chunk_size=32, has_inputs=True, name='ECogFeatCalc', fuse_chain=True):
         super().__init__(name=name, has_inputs=has_inputs)
-        if not warm_start:
-            raise NotImplementedError("only the warm_start=True configuration used by decode.py is implemented")
+        # warm_start=False (no entry point of the reference passes it): the last filter starts cold, frames are cut from the
+        # first sample on, and the stack buffer emits only once it holds model_order * step_size + 1 rows (FrameBuffer.py:91-98)
+        self.warm_start = bool(warm_start)
         self.sample_rate = sample_rate
         self.frame_len_ms = frame_len_ms
         self.frame_shift_ms = frame_shift_ms
@@ -57,10 +58,12 @@ class ECogFeatCalc(Node.Node):
         plan = self._fe.plan
         _lib.check(_lib.lib().sgs_feat_stream_create(_lib.C.byref(h), self._fe.handle(), n_channels, plan.frame_size,
                                                      self.model_order, self.step_size))
+        if not self.warm_start:
+            _lib.check(_lib.lib().sgs_feat_stream_set_cold_start(h, 1))
         self._stream = h
         self._n_channels = n_channels
         self._out = np.empty((16, n_channels * (self.model_order + 1)), dtype=np.float64)
-        if self.fuse_chain:
+        if self.fuse_chain and self.warm_start:          # the fused chain emits every frame; the cold stack buffer withholds the first ones
             from sgs import chain
             nodes = chain.find_chain(self)
             if nodes is not None:
@@ -97,18 +100,18 @@ class ECogFeatCalc(Node.Node):
         (FrameBuffer.py:147-177).  A device push completes at most MAX_FRAMES frames: when more would end inside n_max samples
         (sample rates below ~800 Hz at a 10 ms shift, or a short frame_shift_ms) the push is cut just before the end of the
         first frame that does not fit, so no frame is ever deferred past the samples that complete it."""
-        plan = self._fe.plan
-        base = plan.zero_fill + self._consumed
+        zero_fill = self._fe.plan.zero_fill if self.warm_start else 0
+        base = zero_fill + self._consumed
         n, ends, idx = n_max, [], []
         while self._next_end <= base + n:
             if len(ends) == MAX_FRAMES:
                 n = self._next_end - 1 - base
                 break
-            ends.append(self._next_end - plan.zero_fill)
+            ends.append(self._next_end - zero_fill)
             idx.append(self._frame_count)
             self._frame_count += 1
             self._next_end = self._end_of_frame(self._frame_count)
-        if n < 1 or (ends and ends[-1] + plan.zero_fill > base + n):
+        if n < 1 or (ends and ends[-1] + zero_fill > base + n):
             raise ValueError("frame_shift_ms=%r at sample_rate=%r completes more than %d frames per sample: unsupported"
                              % (self.frame_shift_ms, self.sample_rate, MAX_FRAMES))
         return n, ends, idx
@@ -149,4 +152,5 @@ class ECogFeatCalc(Node.Node):
             self._consumed += n
             pos += n
             for q in range(len(ends)):
-                self.output_data(self._out[q].copy())
+                if self.warm_start or idx[q] >= self.model_order * self.step_size:
+                    self.output_data(self._out[q].copy())

@@ -18,10 +18,11 @@ class GriffinLimSynthesis(Node.Node):
     def __init__(self, originalFrameSizeMs, frameShiftMs, sampleRate, melCoeffCount, numReconstructionIterations=5,
                  extraContext=0, cutoff=7900, normFactor=1.0, useLogMels=True, name='GriffinLim', device_noise=False):
         super().__init__(name=name)
-        if extraContext != 0 or not useLogMels:
-            raise NotImplementedError("only extraContext=0, useLogMels=True (decode.py:162-164) are implemented")
+        if extraContext != 0:
+            raise NotImplementedError("only extraContext=0 (decode.py:162-164) is implemented: a longer block changes the "
+                                      "register layout of the block kernel")
         self._op = GriffinLimNodeOp(originalFrameSizeMs, frameShiftMs, sampleRate, melCoeffCount,
-                                    numReconstructionIterations, cutoff, normFactor)
+                                    numReconstructionIterations, cutoff, normFactor, use_log_mels=useLogMels)
         plan = self._op.plan
         self.useLogMels = useLogMels
         self.frameShiftMs = float(frameShiftMs)

@@ -54,11 +54,13 @@ def _declare(lib):
        c_void_p, c_void_p, c_void_p, c_void_p)
     fn('sgs_feat_stream_create', c_int, C.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int)
     fn('sgs_feat_stream_destroy', None, c_void_p)
+    fn('sgs_feat_stream_set_cold_start', c_int, c_void_p, c_int)
     fn('sgs_feat_stream_push', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p)
     fn('sgs_sos_stream_create', c_int, C.POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int)
     fn('sgs_sos_stream_destroy', None, c_void_p)
     fn('sgs_sos_stream_push', c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p)
     fn('sgs_gl_node_rebase', c_int, c_void_p, C.c_int32)
+    fn('sgs_gl_node_set_log_mels', c_int, c_void_p, c_int)
     fn('sgs_gl_node_push', c_int, c_void_p, c_void_p, c_int, c_void_p, C.c_int32, c_void_p, C.c_uint64, c_void_p,
        C.POINTER(c_int), c_void_p)
     fn('sgs_chain_create', c_int, C.POINTER(c_void_p), c_void_p, c_int, c_void_p, c_void_p)

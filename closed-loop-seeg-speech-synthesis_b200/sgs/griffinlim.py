@@ -22,7 +22,8 @@ class GriffinLimNodeOp:
     """Batched equivalent of GriffinLimSynthesis fed frame by frame (livenodes/GriffinLim.py)."""
 
     def __init__(self, frame_size_ms=16, frame_shift_ms=10, sample_rate=16000, n_mels=40, iterations=5, cutoff=7900,
-                 norm_factor=1.0):
+                 norm_factor=1.0, use_log_mels=True):
+        self.use_log_mels = bool(use_log_mels)
         self.plan = GriffinLimNodePlan(frame_size_ms, frame_shift_ms, sample_rate, n_mels, iterations, 0, cutoff, norm_factor)
         p = self.plan
         self.first_frame = p.block_len - p.context_width - 1
@@ -48,6 +49,8 @@ class GriffinLimNodeOp:
                 _lib.C.byref(h), p.fft_size, p.hop, p.block_len, p.context_width, self.n_mels, _lib.ptr(win), _lib.ptr(ola),
                 _lib.ptr(idx), _lib.ptr(w), _lib.ptr(b), _lib.ptr(a), self.order, _lib.ptr(phi), LP_CHUNK, _lib.ptr(phi_sub),
                 float(p.norm_factor * 1.01), p.iterations))
+            if not self.use_log_mels:
+                _lib.check(_lib.lib().sgs_gl_node_set_log_mels(h, 0))
             self._handle = h
         return self._handle
 

@@ -90,6 +90,11 @@ void sgs_feat_stream_destroy(sgs_feat_stream* s);
 int sgs_feat_stream_push(sgs_feat_stream* s, const void* x, int x_is_f64, int n, const int64_t* frame_ends,
                          const int64_t* frame_index, int n_frames, double* out, void* stream);
 
+/* ECogFeatCalc(warm_start=False), FrameBuffer.py:91-98: the last filter starts from zi * (its first input) like the others
+ * instead of its warm state, and there is no zero fill in front of the stream (frame_ends are then plain sample counts; the
+ * caller also withholds the first order * step stacked rows, as the empty stack FrameBuffer does).  Before the first push. */
+int sgs_feat_stream_set_cold_start(sgs_feat_stream* stream, int cold);
+
 /* Filtering FrameBuffer node (livenodes/FrameBuffer.py:86-143): one scipy.signal.sosfilt cascade (<= 8 sections) over all
  * channels with the state resident between chunks.  sos[n_sections][6], zi[n_sections][2] = sosfilt_zi(sos); the first push
  * starts from zi (warm_start, FrameBuffer.py:95-98 then pushes its zero fill through the same stream) or from zi * x[0]
@@ -174,6 +179,10 @@ int sgs_gl_node_push(sgs_gl_node* node, const double* logmel, int n, const int32
  * (the reference keeps its positions modulo the ring length, GriffinLim.py:115-166, and so runs indefinitely): after the
  * call, pos / pos_before of sgs_gl_node_push and sgs_chain_push are expected in the shifted coordinates. */
 int sgs_gl_node_rebase(sgs_gl_node* node, int32_t delta);
+
+/* GriffinLimSynthesis(useLogMels=...), GriffinLim.py:84-87: 1 (default) takes log-mel frames through fromLogMels (exp, then
+ * non-finite magnitudes -> 0), 0 takes linear mel frames through fromMels.  Applies to the calls that follow. */
+int sgs_gl_node_set_log_mels(sgs_gl_node* node, int log_mels);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused streaming chain: the four nodes decode.py:152-183 wires (ECogFeatCalc -> LDASynthesis -> Dequantization ->

@@ -252,9 +252,39 @@ def gen_griffinlim():
     print('griffinlim.npz', {k: getattr(v, 'shape', v) for k, v in out.items()})
 
 
+def gen_variants():
+    """Constructor options no entry point of the reference passes, run through the unmodified nodes: ECogFeatCalc with
+    warm_start=False (cold last filter, no zero fill, the stack buffer starts empty) and GriffinLimSynthesis with
+    useLogMels=False (linear mel input through fromMels)."""
+    out = {}
+    sr, n_ch = 1024, 6
+    x = synth.seeg_session(61, n_ch, sr, 1.5).astype(np.float64)
+    for ln in (50, 60):
+        src = Node.Node(name='src', has_inputs=False)
+        fe = ECogFeatCalc.ECogFeatCalc(sr, frame_len_ms=50, frame_shift_ms=10, model_order=4, step_size=5, line_noise=ln,
+                                       warm_start=False, chunk_size=32)(src)
+        rows = []
+        fe.add_output(lambda f: rows.append(np.array(f, copy=True)))
+        for i in range(0, len(x), 32):
+            src.output_data(np.array(x[i:i + 32]))
+        out['cold_rows_ln%d' % ln] = np.array(rows)
+    out['cold_session'], out['cold_sr'], out['cold_n_ch'], out['cold_seconds'] = 61, sr, n_ch, 1.5
+    med = synth.default_medians()
+    lin = np.exp(synth.logmel_utterances(1, 12, med, seed=3003)[0])
+    node = GriffinLim.GriffinLimSynthesis(16, 10, 16000, 40, numReconstructionIterations=8, normFactor=10, useLogMels=False)
+    got = []
+    node.add_output(lambda f: got.append(np.array(f, copy=True)))
+    np.random.seed(79)
+    for k in range(len(lin)):
+        node.add_data(lin[k])
+    out['linmel_in'], out['linmel_pcm'], out['linmel_seed'] = lin, np.hstack([g for g in got if len(g)]), 79
+    np.savez_compressed(os.path.join(OUT, 'variants.npz'), **out)
+    print('variants.npz', {k: getattr(v, 'shape', v) for k, v in out.items()})
+
+
 if __name__ == '__main__':
     only = sys.argv[1:]
-    for fn in (gen_features, gen_mel, gen_griffinlim, gen_train_decode, gen_model128):
+    for fn in (gen_features, gen_mel, gen_griffinlim, gen_train_decode, gen_model128, gen_variants):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(OUT)):

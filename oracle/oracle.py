@@ -43,9 +43,10 @@ def _tile_zi(sos, n_ch):
 # a7: filtered stream shared by both feature paths (R1 in SURVEY.md 8a')
 #     offline.py:31-97 ; FrameBuffer.py:86-98,139-143 chained as in ECogFeatCalc.py:67-85
 # --------------------------------------------------------------------------------------------
-def high_gamma_stream(eeg, sr, line_noise=50, window_length=0.05, window_shift=0.01, keep_zero_fill=False):
+def high_gamma_stream(eeg, sr, line_noise=50, window_length=0.05, window_shift=0.01, keep_zero_fill=False, warm_start=True):
     """Returns the notch-filtered high-gamma signal.  With keep_zero_fill the response of the last
-    filter to its warm-start zeros is kept in front (the online node frames over it)."""
+    filter to its warm-start zeros is kept in front (the online node frames over it).  warm_start=False
+    (ECogFeatCalc(warm_start=False), FrameBuffer.py:91-93): the last filter starts cold like the others, no zero fill."""
     data = np.asarray(eeg, dtype=np.float64)
     n_ch = data.shape[1]
     hg = create_filter_sos(sr, 70, 170)
@@ -61,6 +62,10 @@ def high_gamma_stream(eeg, sr, line_noise=50, window_length=0.05, window_shift=0
         st = _tile_zi(f, n_ch) * data[0, :]
         data, _ = scipy.signal.sosfilt(f, data, axis=0, zi=st)
     last = notches[-1]                                                   # warm start (62 / 93)
+    if not warm_start:
+        st = _tile_zi(last, n_ch) * data[0, :]
+        data, _ = scipy.signal.sosfilt(last, data, axis=0, zi=st)
+        return (data, 0) if keep_zero_fill else data
     st = _tile_zi(last, n_ch)
     head, st = scipy.signal.sosfilt(last, zero_fill, axis=0, zi=st)
     data, _ = scipy.signal.sosfilt(last, data, axis=0, zi=st)
@@ -101,7 +106,7 @@ def stack_offline(features, model_order=4, step_size=5):
 #     FrameBuffer.py:60-177, ECogFeatCalc.py:67-104,118-144
 # --------------------------------------------------------------------------------------------
 def ecog_feat_calc(eeg, sr, frame_len_ms=50, frame_shift_ms=10, model_order=4, step_size=5, line_noise=50,
-                   chunk_size=32, stacked=True):
+                   chunk_size=32, stacked=True, warm_start=True):
     """All frames the node chain emits after the whole array has been pushed through it (any
     chunking; the chain is chunk-size invariant for chunks < 2048 samples).
     The first two FrameBuffers forward only complete `chunk_size` blocks, so a trailing partial
@@ -113,7 +118,7 @@ def ecog_feat_calc(eeg, sr, frame_len_ms=50, frame_shift_ms=10, model_order=4, s
     if usable == 0:
         return np.zeros((0, (model_order + 1) * n_ch if stacked else n_ch))
     y2, _ = high_gamma_stream(eeg[:usable], sr, line_noise, frame_len_ms / 1000.0, frame_shift_ms / 1000.0,
-                              keep_zero_fill=True)
+                              keep_zero_fill=True, warm_start=warm_start)
     frame_size = int((float(frame_len_ms) / 1000.0) * sr_f)              # FrameBuffer.py:27
     first_ms = (float(frame_size) / sr_f) * 1000.0                       # FrameBuffer.py:35
     feats = []
@@ -126,6 +131,9 @@ def ecog_feat_calc(eeg, sr, frame_len_ms=50, frame_shift_ms=10, model_order=4, s
     f = np.array(feats).reshape(-1, n_ch)
     if not stacked:
         return f
+    if not warm_start:
+        # the stack FrameBuffer (21 rows / 1 row, FrameBuffer.py:99-100) starts empty: first output with the 21st row
+        return stack_offline(f, model_order, step_size) if len(f) > model_order * step_size else np.zeros((0, (model_order + 1) * n_ch))
     return stack_online(f, model_order, step_size)
 
 
@@ -180,6 +188,9 @@ class MelFilterBank:
 
     def fromLogMels(self, mel_spectrogram):
         return self._normal(np.dot(np.exp(mel_spectrogram), self.melInvMatrix))
+
+    def fromMels(self, mel_spectrogram):
+        return np.dot(mel_spectrogram, self.melInvMatrix)                 # MelFilterBank.py:60-61,75-76: no clean-up
 
 
 # --------------------------------------------------------------------------------------------
@@ -252,7 +263,8 @@ class GriffinLimNode:
     `noise[k]` is the np.random.rand(block_samples) draw of frame k (frames k >= spec_frames-1 draw)."""
 
     def __init__(self, frame_size_ms=16, frame_shift_ms=10, sample_rate=16000, n_mels=40, iterations=8,
-                 cutoff=7900, norm_factor=1.0):
+                 cutoff=7900, norm_factor=1.0, use_log_mels=True):
+        self.use_log_mels = use_log_mels
         fs, sh, sr = float(frame_size_ms), float(frame_shift_ms), float(sample_rate)
         self.sample_rate, self.frame_shift_ms = sr, sh
         self.fft_size = int((fs / 1000.0) * sr)
@@ -271,7 +283,7 @@ class GriffinLimNode:
 
     def block(self, logmel_frames, noise):
         """reconstructWavFromSpectrogram (GriffinLim.py:76-96) incl. quirk Q1 (no 1j in the phase term)."""
-        spec = self.mel.fromLogMels(logmel_frames)
+        spec = self.mel.fromLogMels(logmel_frames) if self.use_log_mels else self.mel.fromMels(logmel_frames)   # GriffinLim.py:84-87
         x = np.array(noise, dtype=np.float64, copy=True)
         n = self.fft_size
         for _ in range(self.iterations):

@@ -19,8 +19,8 @@ def declared_functions():
 
 def test_header_declares_the_hot_path_entry_points():
     names = declared_functions()
-    for must in ('sgs_feat_extract', 'sgs_feat_stack', 'sgs_feat_stream_push', 'sgs_lda_decode', 'sgs_dequantize',
-                 'sgs_gl_node_synthesize', 'sgs_gl_node_push', 'sgs_gl_node_rebase', 'sgs_gl_batch_synthesize', 'sgs_logmel', 'sgs_quantize',
+    for must in ('sgs_feat_extract', 'sgs_feat_stack', 'sgs_feat_stream_push', 'sgs_feat_stream_set_cold_start', 'sgs_lda_decode', 'sgs_dequantize',
+                 'sgs_gl_node_synthesize', 'sgs_gl_node_push', 'sgs_gl_node_rebase', 'sgs_gl_node_set_log_mels', 'sgs_gl_batch_synthesize', 'sgs_logmel', 'sgs_quantize',
                  'sgs_spearman', 'sgs_lda_stats', 'sgs_last_error', 'sgs_init'):
         assert must in names
 

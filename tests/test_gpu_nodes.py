@@ -194,6 +194,43 @@ def test_write_head_rebase_changes_nothing(model, fused, monkeypatch):
     assert len(got[3]) == len(want[3]) > 150 and all(np.array_equal(p, q) for p, q in zip(got[3], want[3]))
 
 
+@pytest.mark.parametrize('ln', [50, 60])
+def test_ecog_feat_calc_cold_start_matches_reference(ln):
+    """ECogFeatCalc(warm_start=False) against the unmodified reference node (tests/golden/variants.npz): cold last filter,
+    frames from the first sample on, no output before the stack buffer holds 21 rows."""
+    from livenodes import Node, ECogFeatCalc
+    G = load('variants.npz')
+    sr, n_ch = int(G['cold_sr']), int(G['cold_n_ch'])
+    x = synth.seeg_session(int(G['cold_session']), n_ch, sr, float(G['cold_seconds'])).astype(np.float64)
+    want = G['cold_rows_ln%d' % ln]
+    for packet in (32, 100):
+        src = Node.Node(name='src', has_inputs=False)
+        fe = ECogFeatCalc.ECogFeatCalc(sr, 50, 10, 4, 5, line_noise=ln, warm_start=False, chunk_size=32)(src)
+        rows = []
+        fe.add_output(lambda f: rows.append(np.array(f, copy=True)))
+        for i in range(0, len(x), packet):
+            src.output_data(np.array(x[i:i + packet]))
+        got = np.array(rows)
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-9
+
+
+def test_griffinlim_linear_mels_match_reference():
+    """GriffinLimSynthesis(useLogMels=False) - linear mel frames through fromMels - against the unmodified reference node."""
+    from livenodes import GriffinLim
+    G = load('variants.npz')
+    lin = G['linmel_in']
+    node = GriffinLim.GriffinLimSynthesis(16, 10, 16000, 40, numReconstructionIterations=8, normFactor=10, useLogMels=False)
+    got = []
+    node.add_output(lambda f: got.append(np.array(f, copy=True)))
+    np.random.seed(int(G['linmel_seed']))
+    for k in range(len(lin)):
+        node.add_data(lin[k])
+    pcm = np.hstack([g for g in got if len(g)])
+    want = G['linmel_pcm']
+    d = np.abs(pcm.astype(int) - want.astype(int))
+    assert pcm.shape == want.shape and d.max() <= 1 and (d > 0).mean() < 2e-3
+
+
 def test_fused_chain_not_used_for_other_wirings(model):
     """A second consumer between the nodes, or a missing node, keeps the per-node path."""
     from livenodes import Node, ECogFeatCalc, LDASynthesis, Dequantization, LambdaNode

@@ -152,3 +152,21 @@ def test_model128_streaming_decode_matches_reference():
     assert np.array_equal(pcm, G['dec_audio'])
     # a trained model: not one class everywhere, and margins much tighter than random weights give
     assert len(np.unique(lab)) >= 5 and G['n_classes'].max() == 9
+
+
+def test_constructor_variants_match_reference():
+    """Options no entry point of the reference passes, pinned against the unmodified nodes (oracle/gen_golden.py:gen_variants):
+    ECogFeatCalc(warm_start=False) - cold last filter, no zero fill, the stack buffer starts empty - and
+    GriffinLimSynthesis(useLogMels=False) - linear mel input through fromMels."""
+    G = load('variants.npz')
+    sr, n_ch = int(G['cold_sr']), int(G['cold_n_ch'])
+    x = synth.seeg_session(int(G['cold_session']), n_ch, sr, float(G['cold_seconds'])).astype(np.float64)
+    for ln in (50, 60):
+        want = G['cold_rows_ln%d' % ln]
+        got = O.ecog_feat_calc(x, sr, 50, 10, 4, 5, ln, 32, warm_start=False)
+        assert got.shape == want.shape and len(want) > 100
+        assert np.abs(got - want).max() <= 4e-15
+    lin = G['linmel_in']
+    node = O.GriffinLimNode(16, 10, 16000, 40, 8, 7900, 10, use_log_mels=False)
+    pcm, _ = node.synthesize(lin, node_noise(int(G['linmel_seed']), len(lin)))
+    assert np.array_equal(pcm, G['linmel_pcm'])
