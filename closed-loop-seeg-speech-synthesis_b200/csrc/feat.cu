@@ -29,7 +29,6 @@
 
 namespace sgs {
 
-template <typename T> __device__ __forceinline__ float ld_f(const T* p) { return (float)__ldg(p); }
 template <typename T> __device__ __forceinline__ double ld_d(const T* p) { return (double)__ldg(p); }
 
 constexpr int kThreads = 128;
@@ -67,7 +66,12 @@ __global__ void k_iir_init(const TIn* __restrict__ x, double* __restrict__ state
 enum { kModeState = 0, kModeFeat = 1 };
 
 constexpr int kStages = 4;                      // warps per CTA = pipeline stages of the cascade
+constexpr int kStagesC = kStages;
 constexpr int kBatch = 16;                      // samples handed from stage to stage per iteration
+#ifndef SGS_LOAD_AFTER
+#define SGS_LOAD_AFTER 2
+#endif
+constexpr int kLoadAfter = SGS_LOAD_AFTER;      // stage 0 issues the next batch's loads after this many samples of the current one
 constexpr int kStreamsPerBlock = 32;            // lane = stream
 
 // barrier among the 4 stage warps of one pipeline (named barrier `id`, 128 threads; id 0 when the CTA is one pipeline)
@@ -81,6 +85,25 @@ __device__ __forceinline__ void pipe_sync(int id) { asm volatile("bar.sync %0, 1
 // (base already includes the lane / stream offset); in == nullptr starts from the zero state.
 struct SegState { const double* in; long long in_stride; double* out; long long out_stride; };
 
+// Sections per stage.  The first stage also loads and converts the input, the last one also keeps the prefix ring and closes
+// the windows (a log per window): with 6 sections each the middle stages waited 23 % of their time at the barrier for those
+// two (barrier stall samples per stage: 1.4 / 5.9 / 5.9 / 0.7 % of the kernel's).
+#ifndef SGS_SPLIT_FIRST
+#define SGS_SPLIT_FIRST 4      // sections of stage 0 per 24
+#endif
+#ifndef SGS_SPLIT_LAST
+#define SGS_SPLIT_LAST 4       // sections of the last stage per 24
+#endif
+__host__ __device__ constexpr int stage_sections(int nb, int stage) {
+    const int first = nb * SGS_SPLIT_FIRST / 24, last = nb * SGS_SPLIT_LAST / 24, mid = nb - first - last;
+    return stage == 0 ? first : stage == kStagesC - 1 ? last : stage == 1 ? (mid + 1) / 2 : mid / 2;
+}
+__host__ __device__ constexpr int stage_first(int nb, int stage) {
+    int f = 0;
+    for (int s = 0; s < stage; ++s) f += stage_sections(nb, s);
+    return f;
+}
+
 template <int NB, bool MONIC, int MODE, int RING, int STAGE, typename TIn>
 __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __restrict__ feat,
                                           const SegState ss, const int* __restrict__ starts,
@@ -88,7 +111,7 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
                                           const FeatGeom& g, double* __restrict__ smem, const int bar_id, const int group,
                                           const bool at_stream_start, const long long t_begin, const int len, const int k_lo,
                                           const int k_hi) {
-    constexpr int BPS = NB / kStages, FIRST = STAGE * BPS;
+    constexpr int BPS = stage_sections(NB, STAGE), FIRST = stage_first(NB, STAGE);
     constexpr bool LAST = STAGE == kStages - 1;
     const int lane = threadIdx.x & 31;
     int stream = group * kStreamsPerBlock + lane;
@@ -116,10 +139,14 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
     // stage 0: input prefetch, one batch ahead, coalesced (32 consecutive channels of one sample per warp load)
     const TIn* xrow = x + (long long)sess * g.session_stride + ch + t_begin * C;
     const long long t_last = g.n_samples - 1 - t_begin;                    // clamp: never read past the session
-    float xq[STAGE == 0 ? kBatch : 1];
+    // The batch being filtered is held as doubles, converted at the END of the iteration that loaded it.  Converting at the
+    // point of use put the F2F of sample 0 on the scoreboard the compiler had just given to the next batch's 16 loads, so the
+    // first DFMA of every iteration waited for DRAM (long_scoreboard on that one instruction: 6.3 % of the kernel's stall
+    // samples, a quarter of stage 0's time - and the other three stages wait for stage 0 at the barrier).
+    double xq[STAGE == 0 ? kBatch : 1];
     if (STAGE == 0) {
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) xq[u] = ld_f(xrow + (long long)(u < t_last ? u : t_last) * C);
+        for (int u = 0; u < kBatch; ++u) xq[u] = ld_d(xrow + (long long)(u < t_last ? u : t_last) * C);
     }
 
     // last stage: prefix-sum ring + window closing (see k_iir_stages header)
@@ -148,49 +175,64 @@ __device__ __forceinline__ void run_stage(const TIn* __restrict__ x, double* __r
         const int bidx = it - STAGE;
         if (bidx >= 0 && bidx < n_batches) {
             const int m0 = bidx * kBatch;                                  // first sample (relative) of this batch
-            float xn[STAGE == 0 ? kBatch : 1];
-            if (STAGE == 0) {
-#pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    const long long m = (long long)m0 + kBatch + u;
-                    xn[u] = ld_f(xrow + (m < t_last ? m : t_last) * C);
-                }
-            }
+            TIn xn[STAGE == 0 ? kBatch : 1];                                // raw samples of the next batch (a float64 recording keeps all its bits)
             const double* in = buf_in + (size_t)((it - 1) & 1) * kBatch * 32 + lane;
             double* out = buf_out + (size_t)(it & 1) * kBatch * 32 + lane;
-            // two half-batches of 8 samples: keeps every stage's loop body (~300 instructions) inside the
-            // per-scheduler instruction cache while the 4 warps of a CTA execute 4 different bodies
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            // one sample through this stage's sections
+            auto step = [&](const int u, double v) {
 #pragma unroll
-                for (int uu = 0; uu < kBatch / 2; ++uu) {
-                    const int u = h * (kBatch / 2) + uu;
-                    double v = (STAGE == 0) ? (double)(h == 0 ? xq[uu] : xq[uu + kBatch / 2]) : in[u * 32];
-#pragma unroll
-                    for (int p = 0; p < BPS; ++p) {
-                        const int i = FIRST + p;
-                        double y;
-                        if (MONIC && (i % kSecPerFilter) != 0) {
-                            y = v + z0[p];
-                            z0[p] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z1[p]));
-                            z1[p] = fma(-cf.c[i][4], y, v);
-                        } else {
-                            y = fma(cf.c[i][0], v, z0[p]);
-                            z0[p] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z1[p]));
-                            z1[p] = fma(-cf.c[i][4], y, cf.c[i][2] * v);
-                        }
-                        v = y;
+                for (int p = 0; p < BPS; ++p) {
+                    const int i = FIRST + p;
+                    double y;
+                    if (MONIC && (i % kSecPerFilter) != 0) {
+                        y = v + z0[p];
+                        z0[p] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z1[p]));
+                        z1[p] = fma(-cf.c[i][4], y, v);
+                    } else {
+                        y = fma(cf.c[i][0], v, z0[p]);
+                        z0[p] = fma(cf.c[i][1], v, fma(-cf.c[i][3], y, z1[p]));
+                        z1[p] = fma(-cf.c[i][4], y, cf.c[i][2] * v);
                     }
-                    if (!LAST) out[u * 32] = v;
-                    else if (MODE == kModeFeat) {
-                        P = fma(v, v, P);
-                        ring[((m0 + u) & (RING - 1)) * 32 + lane] = P;
+                    v = y;
+                }
+                if (!LAST) out[u * 32] = v;
+                else if (MODE == kModeFeat) {
+                    P = fma(v, v, P);
+                    ring[((m0 + u) & (RING - 1)) * 32 + lane] = P;
+                }
+            };
+            if (STAGE == 0) {
+                // Stage 0 runs its (few) sections over the whole batch in one straight line: its coefficients then stay in
+                // uniform registers for the iteration, and the next batch's 16 loads are issued AFTER the first samples.  With
+                // the loads in front, the first DFMA of each half-batch waited for DRAM: the scoreboard of the uniform
+                // coefficient load it needs was shared with the loads just issued (6.6 % of the kernel's stall samples on
+                // that one instruction, a quarter of this stage's time).
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    if (u == kLoadAfter) {
+#pragma unroll
+                        for (int w = 0; w < kBatch; ++w) {
+                            const long long m = (long long)m0 + kBatch + w;
+                            xn[w] = __ldg(xrow + (m < t_last ? m : t_last) * C);
+                        }
+                    }
+                    step(u, xq[u]);
+                }
+            } else {
+                // two half-batches of 8 samples: keeps the stage's loop body inside the per-scheduler instruction cache
+                // while the 4 warps of a pipeline execute 4 different bodies
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int uu = 0; uu < kBatch / 2; ++uu) {
+                        const int u = h * (kBatch / 2) + uu;
+                        step(u, in[u * 32]);
                     }
                 }
             }
             if (STAGE == 0) {
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) xq[u] = xn[u];
+                for (int u = 0; u < kBatch; ++u) xq[u] = (double)xn[u];
             }
             if (LAST && MODE == kModeFeat) {
                 const int done = m0 + kBatch;                              // samples [0, done) have their prefix in the ring
