@@ -42,6 +42,23 @@ def test_online_against_reference_fixture(sr, ln):
         assert np.abs(st - g).max() < TOL
 
 
+def test_float64_recording_keeps_its_bits():
+    """A float64 recording that is NOT representable in float32 (the reference hands float64 arrays around): the offline
+    kernels and the streaming kernel filter it at full precision.  (Until round 2 the offline loader narrowed every sample
+    to float32 first, which no test saw because the synthetic sessions are float32 numbers.)"""
+    sr = 1024
+    rng = np.random.default_rng(3)
+    x = synth.seeg_session(9, 5, sr, 1.2).astype(np.float64) * (1.0 + 1e-5 * rng.standard_normal((int(1.2 * sr), 5)))
+    assert np.abs(x - x.astype(np.float32)).max() > 1e-7 * np.abs(x).max()
+    fe = FeatureExtractor(sr)
+    want = O.herff2016_b(x, sr, skip_stacking=True)
+    assert np.abs(fe.log_power(x) - want).max() < TOL
+    narrowed = O.herff2016_b(x.astype(np.float32).astype(np.float64), sr, skip_stacking=True)
+    assert np.abs(narrowed - want).max() > 100 * TOL                      # what the narrowing cost
+    on = O.ecog_feat_calc(x, sr, 50, 10, 4, 5, 50, 32, stacked=False)
+    assert np.abs(fe.log_power(x, online=True, chunk_size=32) - on).max() < TOL
+
+
 def test_short_and_empty():
     G = load('features.npz')
     x = synth.seeg_session(8, 1, 1024, 0.30)
