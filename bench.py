@@ -609,6 +609,26 @@ def latency_leg(seconds=62.0, paced_seconds=61.0):
     x = synth.seeg_session(5, N_CH, SR, seconds)
     out = {"config": "128 ch @ 2048 Hz float32 packets, decode.setup_decoder graph in-process (3 receivers attached), "
                      "one sgs_chain_push per packet", "seconds": seconds}
+    # SGS_LAT_RT=1 runs the graph thread pinned and SCHED_FIFO (decode.realtime; what was granted is in "scheduling").  Measured
+    # both ways in profiles/latency_tail_r02.txt: the rare 1.5-2 ms frames of the real-time feed appear under either policy.
+    rt = None
+    if os.environ.get('SGS_LAT_RT'):
+        rt = dec_mod.realtime()
+        rt.__enter__()
+    out["scheduling"] = rt.applied if rt is not None else {"policy": "default (SCHED_OTHER), not pinned"}
+    try:
+        _latency_legs(out, dec_mod, Node, synth, ests, select, medians, x, seconds, paced_seconds)
+    finally:
+        if rt is not None:
+            rt.__exit__(None, None, None)
+    out["p50_ms"], out["p99_ms"] = out["packet_64"]["p50_ms"], out["packet_64"]["p99_ms"]
+    return out
+
+
+def _latency_legs(out, dec_mod, Node, synth, ests, select, medians, x, seconds, paced_seconds):
+    import gc
+    import numpy as np
+    import pickle
     for packet in (64, 32):
         src = Node.Node(name='src', has_inputs=False)
         rec_seeg, rec_spec, rec_audio = dec_mod.setup_decoder(src, SR, pickle.dumps(ests), medians, [], select, gl_norm=10,
@@ -690,8 +710,6 @@ def latency_leg(seconds=62.0, paced_seconds=61.0):
                                          "p99_ms": float(np.percentile(pl, 99)), "p99.9_ms": float(np.percentile(pl, 99.9)),
                                          "max_ms": float(pl.max()), "frames_over_1ms": int((pl > 1.0).sum())}
         del src, rec_seeg, rec_spec, rec_audio
-    out["p50_ms"], out["p99_ms"] = out["packet_64"]["p50_ms"], out["packet_64"]["p99_ms"]
-    return out
 
 
 class _PlainEstimator:

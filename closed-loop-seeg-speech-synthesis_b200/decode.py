@@ -203,6 +203,54 @@ def setup_decoder(eeg_sender, sfreq, estimators_serialized, medians_array, bad_c
     return rec_seeg, rec_spec, rec_audio
 
 
+class realtime:
+    """Scheduling of the process that runs the node graph, for the closed-loop (latency) path: pins the calling thread to one
+    core and asks for SCHED_FIFO, as a real-time deployment would; restores both on exit.  Opt-in, and no cure-all: of the
+    3-13 frames per 30 s of real-time feed that take 1.5-2 ms instead of 0.2-0.6 ms (profiles/latency_tail_r02.txt) one run
+    lost all of them under this policy (max 0.57 ms) and the next kept them - they follow the idle GPU / host between packets,
+    not the scheduler class.  Where the process may not change its policy (no CAP_SYS_NICE) it keeps the pinning and says so
+    in `.applied`.
+
+        with decode.realtime():
+            sender.start_processing(...)"""
+
+    def __init__(self, core=None, priority=50):
+        self.core, self.priority, self.applied = core, priority, {}
+
+    def __enter__(self):
+        try:
+            self._affinity = os.sched_getaffinity(0)
+            cores = sorted(self._affinity)
+            core = self.core if self.core is not None else cores[len(cores) // 2]
+            os.sched_setaffinity(0, {core})
+            self.applied['pinned_to'] = core
+        except (AttributeError, OSError) as e:
+            self._affinity = None
+            self.applied['pinned_to'] = 'refused: %s' % e
+        try:
+            self._policy = os.sched_getscheduler(0)
+            self._param = os.sched_getparam(0)
+            os.sched_setscheduler(0, os.SCHED_FIFO, os.sched_param(self.priority))
+            self.applied['policy'] = 'SCHED_FIFO %d' % self.priority
+        except (AttributeError, OSError) as e:
+            self._policy = None
+            self.applied['policy'] = 'refused: %s' % e
+        return self
+
+    def __exit__(self, *exc):
+        if self._policy is not None:
+            try:
+                os.sched_setscheduler(0, self._policy, self._param)
+            except OSError:
+                pass
+        if self._affinity is not None:
+            try:
+                os.sched_setaffinity(0, self._affinity)
+            except OSError:
+                pass
+        return False
+
+
 def _read_datasets(path, names):
     """Datasets `names` of an HDF5 file: through h5py when it is importable, else through the built-in reader of the flat
     layout these files have (sgs/hdf5lite.py); the .npz of the same stem is read when that is what exists (artefacts written

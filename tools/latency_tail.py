@@ -7,10 +7,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [
-    ("default", {}, None),
-    ("no hand-over during the run", {"SGS_RECEIVER_FLUSH_INTERVAL": "1e9", "SGS_RECEIVER_MAX_BATCH": "0"}, None),
-    ("round-1 hand-over (0.25 s, any size)", {"SGS_RECEIVER_MAX_BATCH": "0"}, None),
-    ("default + switch interval 0.2 ms", {}, 2e-4),
+    ("default: time-sharing policy, no hand-over while frames stream", {}, None),
+    ("pinned + SCHED_FIFO (decode.realtime)", {"SGS_LAT_RT": "1"}, None),
+    ("pinned + SCHED_FIFO, hand-over every 0.25 s on a flusher thread, at most 32 frames", {"SGS_LAT_RT": "1", "SGS_RECEIVER_FLUSH_INTERVAL": "0.25"}, None),
+    ("pinned + SCHED_FIFO, round-1 hand-over (0.25 s, any size)", {"SGS_LAT_RT": "1", "SGS_RECEIVER_FLUSH_INTERVAL": "0.25", "SGS_RECEIVER_MAX_BATCH": "0"}, None),
+    ("time-sharing, round-1 hand-over", {"SGS_RECEIVER_FLUSH_INTERVAL": "0.25", "SGS_RECEIVER_MAX_BATCH": "0"}, None),
 ]
 
 if __name__ == '__main__':
@@ -22,10 +23,15 @@ if __name__ == '__main__':
             sys.setswitchinterval(sw)
         r = bench.latency_leg(float(sys.argv[2]), float(sys.argv[2]))
         keep = ("frames", "p50_ms", "p99_ms", "p99.9_ms", "max_ms", "frames_over_1ms")
-        print(json.dumps({k: {q: v[q] for q in keep} for k, v in r.items() if isinstance(v, dict) and "p99_ms" in v}))
+        res = {k: {q: v[q] for q in keep} for k, v in r.items() if isinstance(v, dict) and "p99_ms" in v}
+        res['scheduling'] = r.get('scheduling')
+        print(json.dumps(res))
         sys.exit(0)
     seconds = sys.argv[1] if len(sys.argv) > 1 else "30"
-    for name, env, sw in CASES:
+    only = os.environ.get("SGS_TAIL_CASES")
+    for ci, (name, env, sw) in enumerate(CASES):
+        if only and str(ci) not in only.split(","):
+            continue
         e = dict(os.environ); e.update(env)
         out = subprocess.run([sys.executable, os.path.abspath(__file__), '--child', seconds, str(sw or 0)], env=e, capture_output=True, text=True)
         line = [l for l in out.stdout.splitlines() if l.startswith('{')]
