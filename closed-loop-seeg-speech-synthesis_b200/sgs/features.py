@@ -15,7 +15,12 @@ SM_COUNT = 148
 STREAMS_PER_BLOCK = 32          # csrc/feat.cu: one CTA = 4 stage-warps x 32 streams
 BLOCKS_PER_SM = 3               # co-resident CTAs needed to cover the hand-off latency (measured optimum)
 MIN_CHUNK = 2048                # amortises the window overlap (<= 102 samples) and the carry step
-DEFAULT_TOL = 2.0 ** -70
+# What a state may still contribute after the zero-state warm-up of a time piece, relative to the state: 2^-50 is below
+# fp64's own resolution of the state (2^-52 per operation, summed over the recurrence) and gives a 36 864-sample horizon at
+# 2048 Hz; the 2^-70 of round 1 cost 49 152 samples - a quarter more warm-up work (6.1 -> 4.6 ms per step) for digits
+# that the recurrence's rounding has already lost.  SGS_FEAT_TOL_LOG2 overrides the exponent.
+import os as _os
+DEFAULT_TOL = 2.0 ** float(_os.environ.get('SGS_FEAT_TOL_LOG2', '-50'))
 
 
 class FeatureExtractor:

@@ -83,7 +83,7 @@ def test_chunked_scan_matches_oracle(mode):
         got = fe.log_power(x, chunks=30)                       # 2048-sample chunks << horizon -> Phi carry
         assert fe.scan_plan(len(x), 5, 30)[3] is not None
     elif mode == 'truncated':
-        got = fe.log_power(x, chunks=2)                        # 30720-sample chunks > horizon (23552)
+        got = fe.log_power(x, chunks=2)                        # 30720-sample chunks > horizon (17408)
         assert fe.scan_plan(len(x), 5, 2)[3] is None and fe.scan_plan(len(x), 5, 2)[2] < 30720
     else:
         got = fe.log_power(x, chunks=1)
