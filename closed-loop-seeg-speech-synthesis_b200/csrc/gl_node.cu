@@ -318,7 +318,10 @@ int gl_blocks_run(const double* logmel, const double* noise, unsigned long long 
     const size_t smem = sizeof(double) * kFft + sizeof(cplx) * (kG8SLen + 2 * kG8BufCplx) + (sizeof(double2) + sizeof(int2)) * kG8SLen +
                         sizeof(double) * kEaTabLen + sizeof(G8WarpSmem) * W;
     const long long n_pairs = (n_items + 1) / 2, want = (n_pairs + W - 1) / W;
-    const int grid = (int)(want < 148LL * 4 ? want : 148LL * 4);
+    // grid: 1 / 2 / 4 / 8 / 16 CTAs per SM in all measured 28.13 / 28.04 / 27.96 / 27.89 / 27.75 ms; 8 / 12 / 16 warps per CTA
+    // 31.09 / 28.01 / 27.98 ms - the kernel does not speed up past 12 resident warps, so it is not short of warps
+    static const int grid_mult = getenv("SGS_GL_GRID_MULT") ? atoi(getenv("SGS_GL_GRID_MULT")) : 16;
+    const int grid = (int)(want < 148LL * grid_mult ? want : 148LL * grid_mult);
     const G8Tables t8{tab.window, tab.tw_t, tab.tw_full, tab.inv_idx, tab.inv_w, tab.log_mels};
     static unsigned long long optin = 0;
     SGS_CUDA(smem_optin(k_gl_blocks8<W, 1>, smem, &optin));
