@@ -456,3 +456,15 @@ def test_hdf5lite_interchanges_with_h5py_when_present(tmp_path):
     back = hdf5lite.read(theirs)
     for k, v in data.items():
         assert (back[k].tobytes() == v.tobytes()) if isinstance(v, np.void) else np.array_equal(back[k], v), k
+
+
+def test_realtime_scheduling_is_restored():
+    """decode.realtime pins the calling thread and asks for SCHED_FIFO; whatever it was granted, affinity and policy are back
+    afterwards (and a refusal is reported, not raised)."""
+    import decode
+    before = (os.sched_getaffinity(0), os.sched_getscheduler(0))
+    with decode.realtime() as rt:
+        assert set(rt.applied) == {'pinned_to', 'policy'}
+        if isinstance(rt.applied['pinned_to'], int):
+            assert os.sched_getaffinity(0) == {rt.applied['pinned_to']}
+    assert (os.sched_getaffinity(0), os.sched_getscheduler(0)) == before
