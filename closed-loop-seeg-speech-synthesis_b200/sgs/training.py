@@ -241,6 +241,22 @@ class DeviceOps:
         import torch
         return torch.zeros(shape, dtype=torch.float64, device=like.device)
 
+    def allgather_1d(self, local, n, group=None):
+        """The block_shard pieces of a length-n vector, one per rank, concatenated on every rank (NCCL all-gather of equal
+        padded chunks, then re-packed: the pieces differ in length by at most one)."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        chunk = -(-int(n) // world)
+        buf = torch.zeros(chunk, dtype=local.dtype, device=local.device)
+        buf[:len(local)] = local
+        out = torch.empty(world * chunk, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        sizes = [block_shard(n, r, world) for r in range(world)]
+        if all(hi - lo == chunk for lo, hi in sizes):
+            return out
+        return torch.cat([out[r * chunk:r * chunk + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+
     def index(self, idx, like):
         import torch
         return torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(like.device)
@@ -288,12 +304,19 @@ def sharded_fit(eeg, audio, sfreq_eeg, sfreq_audio, nb_mel_bins=40, nb_intervals
         # every rank needs the whole audio (the target spectrogram is computed replicated), but not over its own PCIe link and
         # out of the one host memory all ranks share: each uploads 1/world of it and the pieces are summed into place over NVLink
         a_lo, a_hi = block_shard(len(audio), rank, world)
-        audio_d = ops.zeros((len(audio),), like=eeg_d)
-        if a_hi > a_lo:
-            audio_d[a_lo:a_hi] = ops.upload(np.asarray(audio)[a_lo:a_hi], np.float64)
+        piece = ops.upload(np.asarray(audio)[a_lo:a_hi], np.float64)
         prof['h2d_bytes'] = int(eeg[:, c0:c1].nbytes + (a_hi - a_lo) * 8)
         lap('h2d_s', t0)
-        prof['audio_allreduce_bytes'], prof['audio_allreduce_s'] = _allreduce_sum_(audio_d, group)
+        t1 = time.perf_counter()
+        if hasattr(ops, 'allgather_1d'):
+            audio_d = ops.allgather_1d(piece, len(audio), group)            # all-gather: 1/world of the all-reduce's traffic
+        else:
+            audio_d = ops.zeros((len(audio),), like=eeg_d)
+            audio_d[a_lo:a_hi] = piece
+            _allreduce_sum_(audio_d, group)
+        ops.sync()
+        prof['audio_allreduce_bytes'], prof['audio_allreduce_s'] = int(len(audio) * 8), time.perf_counter() - t1
+        del piece
         t0 = time.perf_counter()
     else:
         audio_d = ops.upload(audio, np.float64)
