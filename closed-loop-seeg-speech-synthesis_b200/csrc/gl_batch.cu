@@ -210,9 +210,11 @@ k_gl_batch_iter(const double* __restrict__ xin, long long in_stride, double* __r
             const double sk = sa[i], sk2 = sb[i];
             const cplx Za = Ap[ia], Zb = Ap[ib], w = s_twf[k];
             const cplx d = cplx{Za.x - Zb.x, Za.y + Zb.y}, t = cmul(w, d);
-            const double ex = 0.5 * (Za.x + Zb.x), ey = 0.5 * (Za.y - Zb.y);
-            const cplx X1 = cplx{fma(0.5, t.y, ex), fma(-0.5, t.x, ey)};
-            const cplx X2 = cplx{fma(-0.5, t.y, ex), fma(-0.5, t.x, -ey)};
+            // 2 X instead of X: X / |X| does not see the scale, and a factor of two passes through the reciprocal-square-root
+            // seed and the Newton steps of unit_phase exactly - the same bits without the halves
+            const double ex = Za.x + Zb.x, ey = Za.y - Zb.y;
+            const cplx X1 = cplx{ex + t.y, ey - t.x};
+            const cplx X2 = cplx{ex - t.y, -ey - t.x};
             const cplx u1 = unit_phase(X1), u2 = unit_phase(X2);
             const cplx Z1 = cplx{sk * u1.x, sk * u1.y}, Z2 = cplx{sk2 * u2.x, sk2 * u2.y};
             const cplx sm = cplx{Z1.x + Z2.x, Z1.y - Z2.y}, df = cplx{Z1.x - Z2.x, Z1.y + Z2.y};

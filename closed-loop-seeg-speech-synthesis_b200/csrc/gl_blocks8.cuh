@@ -250,10 +250,13 @@ k_gl_blocks8(const double* __restrict__ logmel, const double* __restrict__ noise
                 const int kk = lane0 ? (i < 4 ? 8 + 16 * i : 16 * (i - 3)) : l8 + 16 * i;
                 const cplx w = s_tw_full[kk];
                 const cplx A = U[i], B = V[7 - i];
+                // 2 X instead of X: the angle does not see a positive scale, and a factor of two goes through the reciprocal
+                // seeds and every product of exp(angle) exactly, so the halves (2 DMUL per pair, 4 DFMA that become DADD) can
+                // go without changing a bit of the result
                 const cplx d1 = cplx{A.x - B.x, A.y + B.y}, t1 = cmul(w, d1);
-                const double ex = 0.5 * (A.x + B.x), ey = 0.5 * (A.y - B.y);
-                re[2 * i] = fma(0.5, t1.y, ex);      im[2 * i] = fma(-0.5, t1.x, ey);
-                re[2 * i + 1] = fma(-0.5, t1.y, ex); im[2 * i + 1] = fma(-0.5, t1.x, -ey);
+                const double ex = A.x + B.x, ey = A.y - B.y;
+                re[2 * i] = ex + t1.y;     im[2 * i] = ey - t1.x;
+                re[2 * i + 1] = ex - t1.y; im[2 * i + 1] = -ey - t1.x;
             }
             // (B) exp(angle) of the 16 bins, four at a time
             double ea[16];
