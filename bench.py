@@ -352,7 +352,7 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     step_ms = [(ev0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(args.steps)]
     launches = _lib.launch_count() - n0
-    prof = {k: _lib.profile_read(k) for k in ('iir_init', 'iir_state', 'iir_carry', 'iir_feat', 'iir_pieces_state', 'iir_pieces_feat',
+    prof = {k: _lib.profile_read(k) for k in ('iir_init', 'iir_state', 'iir_carry', 'iir_feat', 'iir_pieces_tail', 'iir_pieces_state', 'iir_pieces_feat',
                                               'lda_pack', 'lda_tc', 'lda', 'gl_blocks', 'gl_ola', 'lowpass')}
     _lib.profile_enable(False)
     spec, audio = out

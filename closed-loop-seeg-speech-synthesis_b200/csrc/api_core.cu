@@ -16,7 +16,7 @@ static cudaEvent_t g_open[kProfCount];
 static double g_prof_ms[kProfCount];
 static unsigned long long g_prof_n[kProfCount];
 static const char* kProfNames[kProfCount] = {"iir_init", "iir_state", "iir_carry", "iir_feat", "stack", "lda", "gl_blocks", "gl_ola",
-                                             "lowpass", "stream", "gl_batch", "logmel", "train", "lda_tc", "train_tc", "iir_pieces_state", "iir_pieces_feat", "lda_pack"};
+                                             "lowpass", "stream", "gl_batch", "logmel", "train", "lda_tc", "train_tc", "iir_pieces_state", "iir_pieces_feat", "lda_pack", "iir_pieces_tail"};
 
 void prof_begin(int id, cudaStream_t st) {
     cudaEvent_t e;

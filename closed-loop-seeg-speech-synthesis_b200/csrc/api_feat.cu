@@ -18,6 +18,10 @@ struct sgs_feat_plan {
     std::vector<int32_t> h_starts;
     int32_t* d_starts = nullptr;
     size_t d_starts_cap = 0;
+    // modal tail of the warm-up (sgs_feat_plan_set_tail)
+    bool has_tail = false;
+    sgs::TailTab tail;
+    double* d_tail_matrix = nullptr;      // [2 n_biquads][2 n_modes]
 };
 
 extern "C" {
@@ -65,7 +69,58 @@ void sgs_feat_plan_destroy(sgs_feat_plan* p) {
     if (p->d_zf) cudaFree(p->d_zf);
     if (p->d_coef) cudaFree(p->d_coef);
     if (p->d_starts) cudaFree(p->d_starts);
+    if (p->d_tail_matrix) cudaFree(p->d_tail_matrix);
     delete p;
+}
+
+int sgs_feat_plan_set_tail(sgs_feat_plan* p, int near_len, int n_modes, const int32_t* mode_len, const double* lam,
+                           const int32_t* warp_blocks, const double* warp_shift, const double* state_matrix, const double* kappa) {
+    using namespace sgs;
+    SGS_ARG(p, "NULL plan");
+    if (n_modes == 0) { p->has_tail = false; return SGS_OK; }
+    SGS_ARG(mode_len && lam && warp_blocks && warp_shift && state_matrix && kappa, "NULL argument");
+    SGS_ARG(n_modes > 0 && n_modes <= kTailMaxModes && n_modes % 4 == 0, "n_modes must be 4, 8, 12 or 16 (got %d)", n_modes);
+    SGS_ARG(near_len >= 64 && near_len % 64 == 0, "near_len must be a positive multiple of 64 (got %d)", near_len);
+    TailTab& t = p->tail;
+    memset(&t, 0, sizeof(t));
+    for (int m = 0; m < n_modes; ++m) {
+        SGS_ARG(mode_len[m] >= 0 && mode_len[m] % kTailBlock == 0, "mode_len[%d] = %d is not a multiple of %d", m, mode_len[m], kTailBlock);
+        SGS_ARG(m == 0 || mode_len[m] <= mode_len[m - 1], "modes must be sorted by length, longest first");
+        SGS_ARG(m % 4 == 0 || mode_len[m] == mode_len[m - 1], "modes join in groups of 4 of equal length");
+        t.mode_blocks[m] = mode_len[m] / kTailBlock;
+        t.lam[m][0] = lam[2 * m];
+        t.lam[m][1] = lam[2 * m + 1];
+        t.rec[m][0] = 2.0 * lam[2 * m];
+        t.rec[m][1] = -(lam[2 * m] * lam[2 * m] + lam[2 * m + 1] * lam[2 * m + 1]);
+        for (int w = 0; w < kTailWarps; ++w) {
+            t.shift[w][m][0] = warp_shift[(w * n_modes + m) * 2];
+            t.shift[w][m][1] = warp_shift[(w * n_modes + m) * 2 + 1];
+        }
+    }
+    // every block of every group belongs to exactly one warp
+    for (int gq = 0; gq < kTailMaxModes / 4; ++gq) {
+        const int blocks = gq * 4 < n_modes ? t.mode_blocks[gq * 4] : 0;
+        std::vector<char> seen(blocks, 0);
+        for (int w = 0; w < kTailWarps; ++w) {
+            const int lo = warp_blocks[(w * (kTailMaxModes / 4) + gq) * 2], hi = warp_blocks[(w * (kTailMaxModes / 4) + gq) * 2 + 1];
+            SGS_ARG(lo >= 0 && lo <= hi && hi <= blocks, "warp %d, group %d: blocks [%d, %d) outside [0, %d)", w, gq, lo, hi, blocks);
+            for (int d = lo; d < hi; ++d) { SGS_ARG(!seen[d], "block %d of group %d dealt twice", d, gq); seen[d] = 1; }
+            t.blk_lo[w][gq] = lo;
+            t.blk_hi[w][gq] = hi;
+        }
+        for (int d = 0; d < blocks; ++d) SGS_ARG(seen[d], "block %d of group %d dealt to no warp", d, gq);
+    }
+    t.n_modes = n_modes;
+    t.near_len = near_len;
+    t.far_len = mode_len[0];
+    const size_t bytes = sizeof(double) * 2 * p->n_biquads * 2 * n_modes;                 // state matrix, then kappa: the same size
+    if (p->d_tail_matrix) { cudaFree(p->d_tail_matrix); p->d_tail_matrix = nullptr; }
+    cudaError_t e = cudaMalloc(&p->d_tail_matrix, 2 * bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_tail_matrix, state_matrix, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((char*)p->d_tail_matrix + bytes, kappa, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { p->has_tail = false; return cuda_fail(e, "tail matrix upload", __FILE__, __LINE__); }
+    p->has_tail = true;
+    return SGS_OK;
 }
 
 int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_samples, int n_channels, int n_sessions,
@@ -176,6 +231,13 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
                     sg.group = (int)grp;
                     sg.t_begin = t0;
                     sg.warm_begin = t0 > horizon ? t0 - horizon : 0;
+                    sg.tail = 0;
+                    if (p->has_tail && t0 >= 2LL * p->tail.near_len) {
+                        // far past as modal sums, cascade over near_len only; 2: the recording starts inside the tail's
+                        // horizon, so the initial state still counts (k_iir_tail)
+                        sg.tail = t0 >= (long long)p->tail.near_len + p->tail.far_len ? 1 : 2;
+                        sg.warm_begin = t0 - p->tail.near_len;
+                    }
                     sg.k_lo = t0 == 0 ? 0 : first_window_at(t0);
                     sg.k_hi = to_end ? n_windows : first_window_at(t1);
                     if (t1 > t0) segs.push_back(sg);
@@ -197,7 +259,8 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
             if (e2 != cudaSuccess) { release(sx, st); release(sf, st); return cuda_fail(e2, "piece tables", __FILE__, __LINE__); }
             // (both tables are far below the 64 KB that the runtime stages synchronously, so the vectors may go out of scope)
             rc = feat_run_pieces(p->n_biquads, p->monic, sx.dev, x_is_f64 != 0, (double*)sf.dev, d_state, d_state + (size_t)ns * g.n_streams,
-                                 (const FeatSeg*)d_tab2, (const int*)(d_tab2 + pf_off), n_pieces, p->d_starts, p->d_zf, p->cf, g, st);
+                                 (const FeatSeg*)d_tab2, (const int*)(d_tab2 + pf_off), n_pieces, (int)segs.size(),
+                                 p->has_tail ? &p->tail : nullptr, p->d_tail_matrix, p->d_starts, p->d_zf, p->cf, g, st);
             if (rc == SGS_OK) rc = finish_out(sf, st);
             cudaFreeAsync(d_tab2, st);
             cudaFreeAsync(d_state, st);

@@ -48,7 +48,7 @@ void release(Staged& s, cudaStream_t st);
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
 enum ProfId { kProfIirInit = 0, kProfIirState, kProfIirCarry, kProfIirFeat, kProfStack, kProfLda, kProfGlBlocks, kProfGlOla,
-              kProfLowpass, kProfStream, kProfGlBatch, kProfLogMel, kProfTrain, kProfLdaTc, kProfTrainTc, kProfPiecesState, kProfPiecesFeat, kProfLdaPack, kProfCount };
+              kProfLowpass, kProfStream, kProfGlBatch, kProfLogMel, kProfTrain, kProfLdaTc, kProfTrainTc, kProfPiecesState, kProfPiecesFeat, kProfLdaPack, kProfPiecesTail, kProfCount };
 extern bool g_prof_on;
 void prof_begin(int id, cudaStream_t st);
 void prof_end(int id, cudaStream_t st);

@@ -358,7 +358,8 @@ k_iir_pieces(const TIn* __restrict__ x, double* __restrict__ feat, const double*
             if (sg.t_begin == 0) continue;                                   // starts from the initial state: nothing to compute
             t_begin = sg.warm_begin;
             len = (int)(sg.t_begin - sg.warm_begin);
-            ss.in = sg.warm_begin == 0 ? init : nullptr; ss.in_stride = g.state_stride;
+            // from the true initial state, from the modal tail sum of the far past (k_iir_tail, same slot), or from zero
+            ss.in = sg.tail ? slot : sg.warm_begin == 0 ? init : nullptr; ss.in_stride = sg.tail ? 32 : g.state_stride;
             ss.out = slot; ss.out_stride = 32;
             at_start = false;
         } else {
@@ -375,6 +376,124 @@ k_iir_pieces(const TIn* __restrict__ x, double* __restrict__ feat, const double*
 }
 #undef SGS_DISPATCH_STAGE
 #undef SGS_RUN_STAGE
+
+// ---- modal tail (sgs/modal.py) -----------------------------------------------------------------------------------------------
+// Start state of a segment's warm-up at t_near = t_begin - near_len from the samples before it: for each of the few modes that
+// outlive near_len, c_m = sum_k lambda_m^k x[t_near - 1 - k] over the mode's own horizon, then state = M (Re c, Im c).  The
+// complex one-pole sum runs as its real second-order form (a damped Goertzel recurrence): y(n) = 2 Re(lambda) y(n-1) -
+// |lambda|^2 y(n-2) + x(n), c = y(n) - conj(lambda) y(n-1) - two FMAs per sample and mode against the cascade's ~99, and only
+// two constants per mode, so every DFMA has a uniform-register operand (a table of 32 powers per mode was tried first: 256
+// distinct constants per block overflow the uniform register file and came back as R2UR moves, one per DFMA).
+// One CTA per segment, lane = stream.  Modes come in groups of 4 with a common length; the (group, block of 32 samples) pairs of
+// all groups, laid end to end, are dealt to the 16 warps in equal runs (cut on the host); a warp runs its blocks oldest first
+// from y = 0, moves its sum to t_near (lambda^(32 first block)), the sums are added in warp order (bit-reproducible) and
+// multiplied by the real 2 nb x 2 n_modes matrix M.
+template <int G, typename TIn>
+__device__ __forceinline__ void tail_group(const TIn* __restrict__ xs, const long long C, const long long t_near, const int d_lo,
+                                           const int d_hi, const int warp, const int lane, double* __restrict__ part, const TailTab& tt) {
+    double y1[4] = {0.0, 0.0, 0.0, 0.0}, y2[4] = {0.0, 0.0, 0.0, 0.0};     // y(n-1), y(n-2)
+    if (d_hi > d_lo) {
+        const TIn* xp = xs + (t_near - (long long)kTailBlock * d_hi) * C;  // blocks d_hi-1 .. d_lo are contiguous in time
+        TIn xv[kTailBlock];
+#pragma unroll
+        for (int j = 0; j < kTailBlock; ++j) { xv[j] = __ldg(xp); xp += C; }
+#pragma unroll 1
+        for (int d = d_hi - 1; d >= d_lo; --d) {
+            double xd[kTailBlock];
+#pragma unroll
+            for (int j = 0; j < kTailBlock; ++j) xd[j] = (double)xv[j];
+            if (d > d_lo) {                                                // the next block's samples, requested before this one's arithmetic
+#pragma unroll
+                for (int j = 0; j < kTailBlock; ++j) { xv[j] = __ldg(xp); xp += C; }
+            }
+#pragma unroll
+            for (int j = 0; j < kTailBlock; ++j) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double y = fma(tt.rec[4 * G + q][0], y1[q], fma(tt.rec[4 * G + q][1], y2[q], xd[j]));
+                    y2[q] = y1[q];
+                    y1[q] = y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int m = 4 * G + q;
+        const double cr = fma(-tt.lam[m][0], y2[q], y1[q]), ci = tt.lam[m][1] * y2[q];    // c = y(n) - conj(lambda) y(n-1)
+        const double sr = tt.shift[warp][m][0], si = tt.shift[warp][m][1];
+        part[(warp * 2 * kTailMaxModes + m) * 32 + lane] = fma(cr, sr, -ci * si);
+        part[(warp * 2 * kTailMaxModes + kTailMaxModes + m) * 32 + lane] = fma(cr, si, ci * sr);
+    }
+}
+
+template <int NS, typename TIn>
+__global__ void __launch_bounds__(kTailWarps * 32, 1)
+k_iir_tail(const TIn* __restrict__ x, double* __restrict__ seg_state /*[segment][NS][32]*/, const FeatSeg* __restrict__ segs,
+           const double* __restrict__ matrix /*[NS][2 n_modes]*/, const double* __restrict__ kappa /*[n_modes][2][NS]*/,
+           const double* __restrict__ init_state /*[NS][streams]*/, const __grid_constant__ TailTab tt,
+           const __grid_constant__ FeatGeom g) {
+    extern __shared__ double smem[];
+    double* part = smem;                                                   // [warp][2 kTailMaxModes][32]
+    double* tot = smem + kTailWarps * 2 * kTailMaxModes * 32;              // [2 kTailMaxModes][32]
+    const FeatSeg sg = segs[blockIdx.x];
+    if (!sg.tail) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int stream = sg.group * kStreamsPerBlock + lane;
+    if (stream >= g.n_streams) stream = g.n_streams - 1;
+    const int sess = stream / g.n_channels, ch = stream - sess * g.n_channels;
+    const long long C = g.n_channels;
+    const long long t_near = sg.t_begin - tt.near_len;
+    const TIn* xs = x + (long long)sess * g.session_stride + ch;
+    // a group this warp has no blocks of contributes exact zeros (lo >= hi).  Nearer to the start of the recording than the
+    // horizon (tail == 2) the blocks before t = 0 do not exist - the state there is the reference's initial state, added below
+    const int have = (int)min(t_near / kTailBlock, (long long)0x7fffffff);
+    tail_group<0, TIn>(xs, C, t_near, tt.blk_lo[warp][0], min(tt.blk_hi[warp][0], have), warp, lane, part, tt);
+    tail_group<1, TIn>(xs, C, t_near, tt.blk_lo[warp][1], min(tt.blk_hi[warp][1], have), warp, lane, part, tt);
+    tail_group<2, TIn>(xs, C, t_near, tt.blk_lo[warp][2], min(tt.blk_hi[warp][2], have), warp, lane, part, tt);
+    tail_group<3, TIn>(xs, C, t_near, tt.blk_lo[warp][3], min(tt.blk_hi[warp][3], have), warp, lane, part, tt);
+    __syncthreads();
+#pragma unroll 1
+    for (int v = warp; v < 2 * kTailMaxModes; v += kTailWarps) {
+        double a = 0.0;
+#pragma unroll 4
+        for (int w = 0; w < kTailWarps; ++w) a += part[(w * 2 * kTailMaxModes + v) * 32 + lane];
+        tot[v * 32 + lane] = a;
+    }
+    __syncthreads();
+    const int nm = tt.n_modes;
+    if (sg.tail == 2) {
+        // c_m += lambda_m^t_near (kappa_m . s_init): what the initial state (k_iir_init) still holds in mode m; warp = mode
+        for (int m = warp; m < nm; m += kTailWarps) {
+            double zr = 1.0, zi = 0.0, br = tt.lam[m][0], bi = tt.lam[m][1];
+            for (long long n = t_near; n; n >>= 1) {                      // lambda^t_near by repeated squaring
+                if (n & 1) { const double t = fma(zr, br, -zi * bi); zi = fma(zr, bi, zi * br); zr = t; }
+                const double t = fma(br, br, -bi * bi); bi = 2.0 * br * bi; br = t;
+            }
+            const double* kr = kappa + (long long)m * 2 * NS;
+            double pr = 0.0, pi = 0.0;
+#pragma unroll 1
+            for (int i = 0; i < NS; ++i) {
+                const double s0 = init_state[(long long)i * g.state_stride + stream];
+                pr = fma(__ldg(kr + i), s0, pr);
+                pi = fma(__ldg(kr + NS + i), s0, pi);
+            }
+            tot[m * 32 + lane] += fma(zr, pr, -zi * pi);
+            tot[(kTailMaxModes + m) * 32 + lane] += fma(zr, pi, zi * pr);
+        }
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int i = warp; i < NS; i += kTailWarps) {
+        const double* row = matrix + (long long)i * 2 * nm;
+        double a = 0.0;
+#pragma unroll 1
+        for (int m = 0; m < nm; ++m) a = fma(__ldg(row + m), tot[m * 32 + lane], a);
+#pragma unroll 1
+        for (int m = 0; m < nm; ++m) a = fma(__ldg(row + nm + m), tot[(kTailMaxModes + m) * 32 + lane], a);
+        seg_state[((long long)blockIdx.x * NS + i) * 32 + lane] = a;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // carry (exact mode): slot j+1 = Phi slot j + e_j for j >= 1, in place; slot 1 is already the true state
@@ -464,7 +583,8 @@ constexpr int kPipes = 4;               // pipelines per CTA (see k_iir_pieces)
 
 template <int NB, bool MONIC, int RING, typename TIn>
 static void run_pieces(const TIn* x, double* feat, double* init_state, double* seg_state, const FeatSeg* segs, const int* piece_first,
-                       int n_pieces, const int* starts, const double* zf, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
+                       int n_pieces, int n_segs, const TailTab* tail, const double* tail_matrix, const int* starts, const double* zf,
+                       const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
     { ProfScope ps(kProfIirInit, st); k_iir_init<NB, TIn><<<ceil_div(g.n_streams, 128), 128, 0, st>>>(x, init_state, cf, g); }
     SGS_LAUNCHED();
     constexpr int hand_bytes = kPipes * (kStages - 1) * 2 * kBatch * 32 * (int)sizeof(double);
@@ -473,6 +593,15 @@ static void run_pieces(const TIn* x, double* feat, double* init_state, double* s
     if (smem_optin(k_iir_pieces<NB, MONIC, kModeFeat, RING, kPipes, TIn>, feat_bytes, &optin_f) != cudaSuccess ||
         smem_optin(k_iir_pieces<NB, MONIC, kModeState, RING, kPipes, TIn>, hand_bytes, &optin_s) != cudaSuccess) return;   // surfaces as the launch error
     const int grid = ceil_div(n_pieces, kPipes);
+    if (tail) {
+        ProfScope ps(kProfPiecesTail, st);
+        constexpr int tail_bytes = (kTailWarps + 1) * 2 * kTailMaxModes * 32 * (int)sizeof(double);
+        static unsigned long long optin_t = 0;
+        if (smem_optin(k_iir_tail<2 * NB, TIn>, tail_bytes, &optin_t) != cudaSuccess) return;
+        k_iir_tail<2 * NB, TIn><<<n_segs, kTailWarps * 32, tail_bytes, st>>>(
+            x, seg_state, segs, tail_matrix, tail_matrix + (size_t)2 * NB * 2 * tail->n_modes, init_state, *tail, g);
+    }
+    if (tail) SGS_LAUNCHED();
     {
         ProfScope ps(kProfPiecesState, st);
         k_iir_pieces<NB, MONIC, kModeState, RING, kPipes, TIn><<<grid, kPipes * kStages * 32, hand_bytes, st>>>(
@@ -489,9 +618,10 @@ static void run_pieces(const TIn* x, double* feat, double* init_state, double* s
 
 template <typename TIn>
 static int run_pieces_typed(int n_biquads, bool monic, const TIn* x, double* feat, double* init_state, double* seg_state,
-                            const FeatSeg* segs, const int* piece_first, int n_pieces, const int* starts, const double* zf,
+                            const FeatSeg* segs, const int* piece_first, int n_pieces, int n_segs, const TailTab* tail,
+                            const double* tail_matrix, const int* starts, const double* zf,
                             const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
-#define SGS_RUN(NB, M, RING) run_pieces<NB, M, RING, TIn>(x, feat, init_state, seg_state, segs, piece_first, n_pieces, starts, zf, cf, g, st)
+#define SGS_RUN(NB, M, RING) run_pieces<NB, M, RING, TIn>(x, feat, init_state, seg_state, segs, piece_first, n_pieces, n_segs, tail, tail_matrix, starts, zf, cf, g, st)
 #define SGS_PICK(NB, M)                                             \
     do {                                                            \
         if (g.window_len + kBatch + 1 <= 128) SGS_RUN(NB, M, 128);  \
@@ -510,13 +640,13 @@ static int run_pieces_typed(int n_biquads, bool monic, const TIn* x, double* fea
 }
 
 int feat_run_pieces(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* init_state, double* seg_state,
-                    const FeatSeg* segs, const int* piece_first, int n_pieces, const int* starts, const double* zf,
-                    const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
+                    const FeatSeg* segs, const int* piece_first, int n_pieces, int n_segs, const TailTab* tail, const double* tail_matrix,
+                    const int* starts, const double* zf, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st) {
     if (x_is_f64)
         return run_pieces_typed<double>(n_biquads, monic, (const double*)x, feat, init_state, seg_state, segs, piece_first, n_pieces,
-                                        starts, zf, cf, g, st);
+                                        n_segs, tail, tail_matrix, starts, zf, cf, g, st);
     return run_pieces_typed<float>(n_biquads, monic, (const float*)x, feat, init_state, seg_state, segs, piece_first, n_pieces,
-                                   starts, zf, cf, g, st);
+                                   n_segs, tail, tail_matrix, starts, zf, cf, g, st);
 }
 
 template <typename TIn>

@@ -42,8 +42,24 @@ struct FeatGeom {
 struct FeatSeg {
     int group;                  // stream group (32 streams)
     int k_lo, k_hi;             // windows owned: those that START inside the segment
+    int tail;                   // 1: the warm-up starts from the modal tail sum k_iir_tail left in the segment's state slot
     long long t_begin;          // first sample of the segment
     long long warm_begin;       // STATE pass: first sample of the warm-up run (0 = from the true initial state)
+};
+
+// Modal tail of the cascade (sgs/modal.py): the few pole pairs that outlive `near_len` samples, summed directly over the far
+// past of a segment start.  Passed BY VALUE (__grid_constant__): the recurrence constants reach the FP64 pipe as uniform
+// operands.  Mode m is live for mode_blocks[m] blocks of kTailBlock samples counted back from t_near = t_begin - near_len;
+// modes are sorted by that length (longest first) and come in groups of 4 of equal length.
+constexpr int kTailBlock = 32, kTailMaxModes = 16, kTailWarps = 16;
+struct TailTab {
+    double rec[kTailMaxModes][2];                    // 2 Re(lambda), -|lambda|^2: the real second-order form of the one-pole sum
+    double lam[kTailMaxModes][2];                    // lambda (re, im)
+    double shift[kTailWarps][kTailMaxModes][2];      // lambda^(32 blk_lo[w][m / 4]): moves warp w's sum to t_near
+    int blk_lo[kTailWarps][kTailMaxModes / 4];       // warp w sums blocks [blk_lo, blk_hi) of mode group g; block 0 ends at t_near
+    int blk_hi[kTailWarps][kTailMaxModes / 4];
+    int mode_blocks[kTailMaxModes];
+    int n_modes, near_len, far_len;
 };
 
 }  // namespace sgs

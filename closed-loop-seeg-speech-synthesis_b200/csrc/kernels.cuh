@@ -16,7 +16,8 @@ int feat_run(int n_biquads, bool monic, const void* x, bool x_is_f64, double* fe
              bool apply_phi, const long long* bounds, const int* kfirst, const int* starts, const double* zf,
              const double* coef, const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st);
 int feat_run_pieces(int n_biquads, bool monic, const void* x, bool x_is_f64, double* feat, double* init_state, double* seg_state,
-                    const FeatSeg* segs, const int* piece_first, int n_pieces, const int* starts, const double* zf,
+                    const FeatSeg* segs, const int* piece_first, int n_pieces, int n_segs, const TailTab* tail /* or nullptr */,
+                    const double* tail_matrix /* device, [2 nb][2 n_modes] */, const int* starts, const double* zf,
                     const FeatCoefs& cf, const FeatGeom& g, cudaStream_t st);
 int stack_run(const double* feat, double* out, int n_sessions, int n_windows, int n_channels, int n_rows, int first_row,
               int order, int step, cudaStream_t st);

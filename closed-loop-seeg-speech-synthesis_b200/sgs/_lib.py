@@ -37,6 +37,7 @@ def _declare(lib):
     fn('sgs_profile_read', c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong))
     fn('sgs_feat_plan_create', c_int, C.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int)
     fn('sgs_feat_plan_destroy', None, c_void_p)
+    fn('sgs_feat_plan_set_tail', c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
     fn('sgs_feat_extract', c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_int, c_int,
        c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p)
     fn('sgs_feat_stack', c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p)

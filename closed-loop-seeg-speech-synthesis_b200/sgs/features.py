@@ -36,6 +36,8 @@ class FeatureExtractor:
         self._horizon = None
         self._phi = {}
         self._tables = {}
+        self._tail = None
+        self._tail_set = False
 
     # -- device plan --------------------------------------------------------------------------
     def handle(self):
@@ -90,6 +92,29 @@ class FeatureExtractor:
                 w += 1024
             self._horizon = w
         return self._horizon
+
+    def tail(self):
+        """Modal tail of the warm-up (sgs/modal.py), or None when switched off (SGS_FEAT_TAIL=0)."""
+        if self._tail is None and os.environ.get('SGS_FEAT_TAIL', '1') != '0':
+            from .modal import ModalTail
+            self._tail = ModalTail(self.plan.coef, self.carry_tol)
+        return self._tail
+
+    def _ensure_tail(self):
+        """Hands the tail tables to the device plan once (only plans that cut time into pieces need them)."""
+        if self._tail_set:
+            return
+        self._tail_set = True
+        t = self.tail()
+        if t is None or t.n_modes == 0:
+            return
+        lam = np.ascontiguousarray(np.stack([t.lam.real, t.lam.imag], axis=1))
+        shift = np.ascontiguousarray(np.stack([t.warp_shift.real, t.warp_shift.imag], axis=2))
+        mode_len = np.ascontiguousarray(t.mode_len, dtype=np.int32)
+        kappa = np.ascontiguousarray(np.stack([t.kappa.real, t.kappa.imag], axis=1))
+        _lib.check(_lib.lib().sgs_feat_plan_set_tail(self.handle(), t.near_len, t.n_modes, _lib.ptr(mode_len), _lib.ptr(lam),
+                                                     _lib.ptr(t.warp_blocks), _lib.ptr(shift), _lib.ptr(t.state_matrix),
+                                                     _lib.ptr(kappa)))
 
     def phi(self, chunk_len):
         if chunk_len not in self._phi:
@@ -168,6 +193,8 @@ class FeatureExtractor:
             out = np.empty((S, nw, Cn), dtype=np.float64)
         if nw > 0 and T > 0:
             k, clen, w, phi = self.scan_plan(T, S * Cn, chunks, horizon)
+            if k > 1 and phi is None:
+                self._ensure_tail()
             _lib.check(_lib.lib().sgs_feat_extract(self.handle(), _lib.ptr(x), int(is64), T, Cn, S, 0, _lib.ptr(starts), nw,
                                                    wl, k, clen, w, _lib.ptr(phi), _lib.ptr(out), _lib.current_stream(x)))
         return out[0] if squeeze else out

@@ -36,9 +36,9 @@ int sgs_synchronize(void* stream);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long sgs_launch_count(void);
 /* Per-kernel-class device time, measured with CUDA events on the launching stream (bench.py's roofline leg).
- * Enable, run, then read: name in {iir_init, iir_state, iir_carry, iir_feat, iir_pieces_state, iir_pieces_feat, stack, lda,
+ * Enable, run, then read: name in {iir_init, iir_state, iir_carry, iir_feat, iir_pieces_tail, iir_pieces_state, iir_pieces_feat, stack, lda,
  * lda_pack, lda_tc, gl_blocks, gl_ola, lowpass, stream, gl_batch, logmel, train, train_tc}.  iir_state / iir_feat are the
- * (stream group x time chunk) grid of the feature scan, iir_pieces_* its balanced-pieces form (large jobs): the launch count
+ * (stream group x time chunk) grid of the feature scan, iir_pieces_* its balanced-pieces form (large jobs; _tail = the modal sums of sgs_feat_plan_set_tail): the launch count
  * of a class tells which decomposition a call took. */
 int sgs_profile_enable(int on);
 int sgs_profile_read(const char* name, double* total_ms, unsigned long long* launches);
@@ -57,6 +57,23 @@ typedef struct sgs_feat_plan sgs_feat_plan;
 int sgs_feat_plan_create(sgs_feat_plan** plan, int n_filters, const double* coef, const double* zi_unit,
                          const double* zi_last_warm, const double* zero_fill_response, int zero_fill);
 void sgs_feat_plan_destroy(sgs_feat_plan* plan);
+
+/* Modal tail of the warm-up (optional; sgs/modal.py derives it from the same coefficients).  A time piece of a large job
+ * starts from the state the cascade had there; without a tail that state comes from running all sections over `horizon`
+ * samples from zero.  With it, only the last near_len samples go through the cascade, started from
+ * state_matrix (Re c, Im c) with c[m] = sum_k lambda[m]^k x[t - 1 - k] over k < mode_len[m] - one complex geometric sum for
+ * each of the n_modes (4, 8, 12 or 16; 0 removes the tail) pole pairs that outlive near_len samples.  Restates what
+ * scipy.signal.sosfilt's state holds after a long run (local/offline.py:63-97) to the tolerance the tables were built for.
+ * mode_len[n_modes]: multiples of 32, longest first, equal within groups of 4.  lam[n_modes][2] = lambda (re, im; a padding
+ * mode is 0).  warp_blocks[16][4][2] = the blocks [lo, hi) of 32 samples (block 0 ends at t - near_len) of each mode group
+ * that each of the kernel's 16 warps sums - every block of a group exactly once, a warp's blocks of one group contiguous;
+ * warp_shift[16][n_modes][2] = lambda^(32 lo) of the mode's group.  state_matrix[2 n_biquads][2 n_modes], row-major.
+ * kappa[n_modes][2][2 n_biquads] (re row, im row): what a state s leaves in mode m, lambda^n (kappa[m] . s) after n samples -
+ * a piece that starts nearer to the beginning of the recording than the longest mode_len sums what samples there are and
+ * takes the rest from the reference's initial state (local/offline.py:39-62). */
+int sgs_feat_plan_set_tail(sgs_feat_plan* plan, int near_len, int n_modes, const int32_t* mode_len, const double* lam,
+                           const int32_t* warp_blocks, const double* warp_shift, const double* state_matrix,
+                           const double* kappa);
 
 /* x: [n_sessions][n_samples][n_channels] (fp32 if x_is_f64 == 0, else fp64), sessions `session_stride`
  *    elements apart (0 = dense).

@@ -115,6 +115,40 @@ def test_device_resident_tensors():
     assert np.abs(st.cpu().numpy() - want).max() < TOL
 
 
+@pytest.mark.parametrize('sr,ln,seconds,n_sess,pieces,check', [
+    (1024, 50, 260.0, 3, 4, 1), (2048, 60, 130.0, 3, 4, 1),
+    # 3 stream groups x 64 000 samples in 5 pieces: the cut at 76 800 starts group 1 at t = 12 800, inside the tail's horizon
+    # (14 912), where the reference's initial state still counts (kappa, sgs/modal.py); session 3 lies in that group
+    (1024, 50, 62.5, 6, 5, 3)])
+def test_modal_tail_equals_the_zero_state_warm_up(sr, ln, seconds, n_sess, pieces, check, monkeypatch):
+    """A piece's start state from the modal sums of the far past + a short cascade run (k_iir_tail, sgs/modal.py) against the
+    full-length zero-state warm-up of the same pieces, and against the oracle."""
+    import torch
+    from sgs import _lib
+    n_ch = 12
+    xs = np.stack([synth.seeg_session(90 + s, n_ch, sr, seconds) for s in range(n_sess)])
+    xd = torch.from_numpy(xs).cuda()
+    monkeypatch.setenv('SGS_FEAT_PIECES', '1')
+    monkeypatch.setenv('SGS_FEAT_PIECES_P', str(pieces))
+    out, launches = {}, {}
+    for tail in ('0', '1'):
+        monkeypatch.setenv('SGS_FEAT_TAIL', tail)
+        fe = FeatureExtractor(sr, line_noise=ln)
+        fe.log_power(xd, chunks=3)                                       # plan + tables
+        n0 = _lib.launch_count()
+        out[tail] = fe.log_power(xd, chunks=3).cpu().numpy()
+        launches[tail] = _lib.launch_count() - n0
+        if tail == '1':
+            t = fe.tail()
+            assert t is not None and t.horizon < len(xs[0]) // 2 and t.near_len < fe.horizon() // 4
+    assert launches['1'] == launches['0'] + 1, launches                  # the tail kernel ran
+    err = np.abs(out['1'] - out['0']).max()
+    print('modal tail vs zero-state warm-up: max |diff| %.3g in log-power' % err)
+    assert err < 2e-11
+    want = O.herff2016_b(xs[check].astype(np.float64), sr, skip_stacking=True, line_noise=ln)
+    assert np.abs(out['1'][check] - want).max() < TOL
+
+
 @pytest.mark.parametrize('online', [False, True])
 def test_balanced_pieces_equal_chunked_scan(online, monkeypatch):
     """The piece decomposition (time lines of all stream groups laid end to end, cut into equal pieces, one or two

@@ -34,3 +34,11 @@ for ch in a.chunks.split(','):
     print('chunks=%s plan=(K=%d L=%d W=%d phi=%s) %.2f ms  %.1f Gsamples/s  in=%.0f GB/s  ch-s/s=%.3g  DFMA-equiv=%.2f T/s (x%.2f work)' % (
         ch, plan[0], plan[1], plan[2], plan[3] is not None, best, samples / best / 1e6, samples * 4 / best / 1e6,
         a.sessions * a.channels * a.dur / (best / 1e3), samples * 100 * cost / best / 1e9, cost), flush=True)
+    _lib.profile_enable(True)
+    fe.log_power(x, chunks=chunks); torch.cuda.synchronize()
+    print('   classes (ms): ' + ', '.join('%s %.3f' % (k, _lib.profile_read(k)[0]) for k in
+                                          ('iir_init', 'iir_pieces_tail', 'iir_pieces_state', 'iir_pieces_feat', 'iir_state', 'iir_feat')), flush=True)
+    _lib.profile_enable(False)
+t = fe.tail()
+if t is not None:
+    print('tail: near %d far %d modes %d lens %s' % (t.near_len, t.far_len, t.n_modes, sorted(set(t.mode_len.tolist()))))
