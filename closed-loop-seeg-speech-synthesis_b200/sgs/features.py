@@ -96,8 +96,8 @@ class FeatureExtractor:
     def tail(self):
         """Modal tail of the warm-up (sgs/modal.py), or None when switched off (SGS_FEAT_TAIL=0)."""
         if self._tail is None and os.environ.get('SGS_FEAT_TAIL', '1') != '0':
-            from .modal import ModalTail
-            self._tail = ModalTail(self.plan.coef, self.carry_tol)
+            from .modal import modal_tail
+            self._tail = modal_tail(self.plan.coef, self.carry_tol)
         return self._tail
 
     def _ensure_tail(self):
