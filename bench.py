@@ -115,7 +115,11 @@ def check_decompositions(decoder, x, _lib):
     torch.cuda.synchronize()
     ran = {k: _lib.profile_read(k)[1] for k in ('iir_pieces_state', 'iir_pieces_feat', 'iir_state', 'iir_feat', 'lda_pack', 'lda_tc')}
     s = x.shape[0] // 2
-    lp1 = decoder.features.log_power(x[s:s + 1], online=True, chunk_size=64)          # one session: the (group x chunk) grid
+    os.environ['SGS_FEAT_PIECES'] = '0'                                                # one session through the (group x chunk) grid
+    try:
+        lp1 = decoder.features.log_power(x[s:s + 1], online=True, chunk_size=64)
+    finally:
+        del os.environ['SGS_FEAT_PIECES']
     torch.cuda.synchronize()
     ran1 = {k: _lib.profile_read(k)[1] - ran[k] for k in ('iir_pieces_feat', 'iir_feat')}
     _lib.profile_enable(False)

@@ -209,7 +209,11 @@ int sgs_feat_extract(sgs_feat_plan* p, const void* x, int x_is_f64, int64_t n_sa
         piece_len = (piece_len + 63) / 64 * 64;
         const char* env = getenv("SGS_FEAT_PIECES");
         const bool want = !(env && env[0] == '0');
-        if (want && !apply_phi && n_chunks > 1 && horizon % 64 == 0 && piece_len >= 2LL * horizon && piece_len <= n_samples) {
+        // a cut costs a warm-up: pieces of at least twice the zero-state horizon, or - with the modal tail, whose cascade run is
+        // near_len samples - of at least 4 near_len (SGS_FEAT_PIECES_MINLEN overrides, for measurements)
+        long long min_len = p->has_tail ? 4LL * p->tail.near_len : 2LL * horizon;
+        if (const char* env_m = getenv("SGS_FEAT_PIECES_MINLEN")) { if (atoll(env_m) > 0) min_len = atoll(env_m); }
+        if (want && !apply_phi && n_chunks > 1 && horizon % 64 == 0 && piece_len >= min_len && piece_len <= n_samples) {
             std::vector<FeatSeg> segs;
             std::vector<int> piece_first;
             auto first_window_at = [&](long long t) {                        // first window whose start is >= t

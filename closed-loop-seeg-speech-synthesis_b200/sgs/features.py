@@ -97,7 +97,10 @@ class FeatureExtractor:
         """Modal tail of the warm-up (sgs/modal.py), or None when switched off (SGS_FEAT_TAIL=0)."""
         if self._tail is None and os.environ.get('SGS_FEAT_TAIL', '1') != '0':
             from .modal import modal_tail
-            self._tail = modal_tail(self.plan.coef, self.carry_tol)
+            try:
+                self._tail = modal_tail(self.plan.coef, self.carry_tol)
+            except ImportError:                   # no mpmath: the device keeps the zero-state warm-up over the whole horizon
+                self._tail = None
         return self._tail
 
     def _ensure_tail(self):
@@ -116,6 +119,18 @@ class FeatureExtractor:
                                                      _lib.ptr(t.warp_blocks), _lib.ptr(shift), _lib.ptr(t.state_matrix),
                                                      _lib.ptr(kappa)))
 
+    def pieces_with_tail(self, n_samples, n_streams):
+        """Whether csrc/api_feat.cu cuts this job into 4 x SM-count balanced pieces on the strength of the modal tail alone."""
+        if os.environ.get('SGS_FEAT_PIECES', '1') == '0' or os.environ.get('SGS_FEAT_PIECES_P'):
+            return False
+        t = self.tail()
+        if t is None or t.n_modes == 0 or self.horizon() % 64:
+            return False
+        groups = -(-n_streams // STREAMS_PER_BLOCK)
+        piece_len = -(-(-(-groups * n_samples // (4 * SM_COUNT))) // 64) * 64
+        min_len = int(os.environ.get('SGS_FEAT_PIECES_MINLEN', 0)) or 4 * t.near_len
+        return min_len <= piece_len <= n_samples and n_samples >= 128
+
     def phi(self, chunk_len):
         if chunk_len not in self._phi:
             self._phi[chunk_len] = np.ascontiguousarray(propagate(self.transition(), int(chunk_len)))
@@ -125,6 +140,10 @@ class FeatureExtractor:
         """(n_chunks, chunk_len, horizon, phi-or-None)."""
         chunks = chunks if chunks is not None else os.environ.get('SGS_FEAT_CHUNKS')
         explicit = chunks
+        if chunks is None and horizon is None and self.pieces_with_tail(n_samples, n_streams):
+            # balanced pieces (csrc/api_feat.cu takes them for any 2-chunk plan without phi when the pieces are long enough for
+            # the modal tail): the same condition as there, so that the (group x chunk) grid never sees this 2-chunk plan
+            return 2, -(-(-(-n_samples // 2)) // 64) * 64, self.horizon(), None
         if chunks is None:
             groups = -(-n_streams // STREAMS_PER_BLOCK)
             want = max(1, int(round(SM_COUNT * BLOCKS_PER_SM / groups)))

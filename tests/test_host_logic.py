@@ -51,7 +51,12 @@ def test_known_constants():
     assert len(g.lp_a) == 6 and abs(g.lp_a[1] - 4.87292) < 1e-4 and g.window[0] < 0
 
 
-def test_scan_plan_modes():
+def test_scan_plan_modes(monkeypatch):
+    fe = FeatureExtractor(2048)
+    k, clen, hor, phi = fe.scan_plan(1228800, 4096)
+    assert k == 2 and hor < clen and phi is None and hor % 1024 == 0            # balanced pieces with the modal tail
+    assert fe.pieces_with_tail(1228800, 128) and not fe.pieces_with_tail(307200, 64)
+    monkeypatch.setenv('SGS_FEAT_TAIL', '0')
     fe = FeatureExtractor(2048)
     k, clen, hor, phi = fe.scan_plan(1228800, 4096)
     assert k == 3 and hor < clen and phi is None and hor % 1024 == 0            # truncated zero-state pass
